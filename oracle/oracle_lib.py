@@ -104,7 +104,12 @@ class DenseFock:
                                  ctypes.byref(self.ready), _p(G))
         return G
 
-    def uhf(self, P1: np.ndarray, P2: np.ndarray) -> np.ndarray:
+    def uhf(self, Pa: np.ndarray, Pb: np.ndarray):
+        """(G_alpha, G_beta): the two calls of uhf.rs:90-91 (both see the old densities)."""
+        return self.uhf_one(Pa, Pb), self.uhf_one(Pb, Pa)
+
+    def uhf_one(self, P1: np.ndarray, P2: np.ndarray) -> np.ndarray:
+        """uhf.rs:210-227 for one spin: density_one = P1, density_two = P2."""
         G = _mat(self.n)
         P1 = np.ascontiguousarray(P1, dtype=np.float64); P2 = np.ascontiguousarray(P2, dtype=np.float64)
         lib().orc_fock_uhf_dense(ctypes.c_int(self.n), _p(P1), _p(P2), _p(self.eri), _p(G))

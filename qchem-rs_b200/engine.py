@@ -1,0 +1,184 @@
+"""ctypes binding of libqcfock.so (include/qcfock.h) and the `FockEngine` wrapper the SCF drivers use.
+
+This is the Python image of the Rust shim SURVEY.md 8b describes (`qcfock-sys` + a safe `FockEngine`
+with Drop and Result): same entry points, same error convention.  There is no CPU fallback: if the
+library is missing or no CUDA device is usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from .basis import CBasis, FlatBasis
+
+_HERE = Path(__file__).resolve().parent
+_SO = _HERE / "libqcfock.so"
+_LIB = None
+_dp = ctypes.POINTER(ctypes.c_double)
+
+QCF_TAU_NONE = -1.0
+
+EXPORTS = ["qcf_create", "qcf_nbasis", "qcf_build_rhf", "qcf_build_uhf", "qcf_build_jk", "qcf_build_rhf_dev",
+           "qcf_build_uhf_dev", "qcf_eri_quartet", "qcf_schwarz", "qcf_boys", "qcf_fp64_peak", "qcf_stats",
+           "qcf_last_error", "qcf_destroy"]
+
+
+class FockError(RuntimeError):
+    pass
+
+
+class COpts(ctypes.Structure):
+    _fields_ = [("screen_tau", ctypes.c_double), ("device", ctypes.c_int), ("rank", ctypes.c_int),
+                ("world_size", ctypes.c_int), ("block_threads", ctypes.c_int)]
+
+
+class CStats(ctypes.Structure):
+    _fields_ = [("n_basis", ctypes.c_int), ("n_shells", ctypes.c_int), ("n_pairs", ctypes.c_int),
+                ("n_groups", ctypes.c_int), ("quartets", ctypes.c_longlong), ("quartets_total", ctypes.c_longlong),
+                ("model_flops", ctypes.c_double), ("kernel_ms", ctypes.c_double), ("total_ms", ctypes.c_double),
+                ("launches", ctypes.c_int)]
+
+
+def build_library(force: bool = False, jobs: int = 8) -> Path:
+    """Compile libqcfock.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-C", str(_HERE / "csrc"), f"-j{jobs}", "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not _SO.exists():
+            raise FockError(f"{_SO} is missing: build it with `make -C qchem-rs_b200/csrc` "
+                            "(there is no CPU fallback)")
+        L = ctypes.CDLL(str(_SO))
+        L.qcf_last_error.restype = ctypes.c_char_p
+        L.qcf_last_error.argtypes = [ctypes.c_void_p]
+        L.qcf_destroy.argtypes = [ctypes.c_void_p]
+        L.qcf_destroy.restype = None
+        L.qcf_create.argtypes = [ctypes.POINTER(CBasis), ctypes.POINTER(COpts), ctypes.POINTER(ctypes.c_void_p)]
+        L.qcf_nbasis.argtypes = [ctypes.c_void_p]
+        L.qcf_build_rhf.argtypes = [ctypes.c_void_p, _dp, _dp]
+        L.qcf_build_uhf.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp]
+        L.qcf_build_jk.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(_dp), ctypes.POINTER(_dp), ctypes.POINTER(_dp)]
+        L.qcf_build_rhf_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.qcf_build_uhf_dev.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5
+        L.qcf_eri_quartet.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [_dp]
+        L.qcf_schwarz.argtypes = [ctypes.c_void_p, _dp]
+        L.qcf_boys.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _dp, _dp]
+        L.qcf_fp64_peak.argtypes = [ctypes.c_void_p, _dp]
+        L.qcf_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(CStats)]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+class FockEngine:
+    """Owns a `qcf_ctx`.  `rhf(P)` / `uhf(Pa, Pb)` are the per-iteration calls that stand in for
+    rhf.rs:67-68 and uhf.rs:90-91."""
+
+    def __init__(self, system_or_flat, tau: float = 0.0, device: int = 0, rank: int = 0, world_size: int = 1,
+                 block_threads: int = 0):
+        self.fb = system_or_flat if isinstance(system_or_flat, FlatBasis) else system_or_flat.flat()
+        self.n = self.fb.n_basis
+        self._lib = lib()
+        self._ctx = ctypes.c_void_p()
+        opts = COpts(tau, device, rank, world_size, block_threads)
+        rc = self._lib.qcf_create(self.fb.ref(), ctypes.byref(opts), ctypes.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.qcf_last_error(self._ctx).decode() if self._ctx else "qcf_create failed"
+            if self._ctx:
+                self._lib.qcf_destroy(self._ctx)
+                self._ctx = ctypes.c_void_p()
+            raise FockError(f"qcf_create: {msg} (code {rc})")
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc != 0:
+            raise FockError(f"{what}: {self._lib.qcf_last_error(self._ctx).decode()} (code {rc})")
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.qcf_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._ctx
+
+    # -- Fock builds --------------------------------------------------------------------------------
+    def rhf(self, P: np.ndarray) -> np.ndarray:
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        G = np.empty((self.n, self.n), dtype=np.float64)
+        self._check(self._lib.qcf_build_rhf(self._ctx, _p(P), _p(G)), "qcf_build_rhf")
+        return G
+
+    def uhf(self, Pa: np.ndarray, Pb: np.ndarray):
+        Pa = np.ascontiguousarray(Pa, dtype=np.float64)
+        Pb = np.ascontiguousarray(Pb, dtype=np.float64)
+        Ga = np.empty((self.n, self.n)); Gb = np.empty((self.n, self.n))
+        self._check(self._lib.qcf_build_uhf(self._ctx, _p(Pa), _p(Pb), _p(Ga), _p(Gb)), "qcf_build_uhf")
+        return Ga, Gb
+
+    def jk(self, dens):
+        nd = len(dens)
+        dens = [np.ascontiguousarray(P, dtype=np.float64) for P in dens]
+        J = [np.empty((self.n, self.n)) for _ in range(nd)]
+        K = [np.empty((self.n, self.n)) for _ in range(nd)]
+        arr = lambda xs: (_dp * nd)(*[_p(x) for x in xs])
+        self._check(self._lib.qcf_build_jk(self._ctx, nd, arr(dens), arr(J), arr(K)), "qcf_build_jk")
+        return J, K
+
+    def rhf_dev(self, dP_ptr: int, dG_ptr: int, stream: int = 0):
+        self._check(self._lib.qcf_build_rhf_dev(self._ctx, dP_ptr, dG_ptr, stream), "qcf_build_rhf_dev")
+
+    def uhf_dev(self, dPa: int, dPb: int, dGa: int, dGb: int, stream: int = 0):
+        self._check(self._lib.qcf_build_uhf_dev(self._ctx, dPa, dPb, dGa, dGb, stream), "qcf_build_uhf_dev")
+
+    # -- parity / diagnostics -----------------------------------------------------------------------
+    def eri_quartet(self, a, b, c, d) -> np.ndarray:
+        nc = lambda l: (l + 1) * (l + 2) // 2
+        shp = tuple(nc(int(self.fb.shell_l[s])) for s in (a, b, c, d))
+        out = np.zeros(shp)
+        self._check(self._lib.qcf_eri_quartet(self._ctx, int(a), int(b), int(c), int(d), _p(out)), "qcf_eri_quartet")
+        return out
+
+    def schwarz(self) -> np.ndarray:
+        ns = len(self.fb.shell_l)
+        Q = np.zeros((ns, ns))
+        self._check(self._lib.qcf_schwarz(self._ctx, _p(Q)), "qcf_schwarz")
+        return Q
+
+    def boys(self, mmax: int, T) -> np.ndarray:
+        T = np.ascontiguousarray(np.atleast_1d(T), dtype=np.float64)
+        F = np.zeros((len(T), mmax + 1))
+        self._check(self._lib.qcf_boys(self._ctx, mmax, len(T), _p(T), _p(F)), "qcf_boys")
+        return F
+
+    def fp64_peak_tflops(self) -> float:
+        v = ctypes.c_double()
+        self._check(self._lib.qcf_fp64_peak(self._ctx, ctypes.byref(v)), "qcf_fp64_peak")
+        return v.value
+
+    def stats(self) -> dict:
+        st = CStats()
+        self._check(self._lib.qcf_stats(self._ctx, ctypes.byref(st)), "qcf_stats")
+        return {k: getattr(st, k) for k, _ in CStats._fields_}

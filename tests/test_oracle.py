@@ -104,8 +104,8 @@ def test_dense_equals_direct_at_tau_zero_rhf_and_uhf():
     np.testing.assert_allclose(direct.rhf(P), dense.rhf(P), atol=1e-11)
     Pa, Pb = random_symmetric_density(n, 2), random_symmetric_density(n, 3)
     Ga, Gb = direct.uhf(Pa, Pb)
-    np.testing.assert_allclose(Ga, dense.uhf(Pa, Pb), atol=1e-11)
-    np.testing.assert_allclose(Gb, dense.uhf(Pb, Pa), atol=1e-11)
+    np.testing.assert_allclose(Ga, dense.uhf_one(Pa, Pb), atol=1e-11)
+    np.testing.assert_allclose(Gb, dense.uhf_one(Pb, Pa), atol=1e-11)
 
 
 def test_schwarz_bounds_every_integral():
