@@ -87,6 +87,11 @@ int qcf_build_jk(qcf_ctx* ctx, int nd, const double* const* P, double* const* J,
 int qcf_build_rhf_dev(qcf_ctx* ctx, const double* dP, double* dG, void* stream);
 int qcf_build_uhf_dev(qcf_ctx* ctx, const double* dPa, const double* dPb, double* dGa, double* dGb, void* stream);
 
+/* One-electron matrices S (overlap), T (kinetic), V (nuclear attraction, charges Z), N x N each.
+ * Replaces molint::overlap / kinetic / nuclear (rhf.rs:41-43, uhf.rs:52-54), so that a driver linked
+ * against this library no longer needs the absent molint crate. */
+int qcf_one_electron(qcf_ctx* ctx, double* S, double* T, double* V);
+
 /* Contracted two-electron integrals of one shell quartet, out[na*nb*nc*nd] row-major (ab|cd),
  * fully normalised.  Computed by the same device code as the Fock build (parity tests). */
 int qcf_eri_quartet(qcf_ctx* ctx, int sa, int sb, int sc, int sd, double* out);
@@ -99,6 +104,18 @@ int qcf_boys(qcf_ctx* ctx, int mmax, int n, const double* T, double* F);
 int qcf_fp64_peak(qcf_ctx* ctx, double* tflops);
 
 int qcf_stats(const qcf_ctx* ctx, qcf_stats_t* out);
+
+/* Per-launch record of the last build: class (la lb|lc ld), primitive-pair counts, list lengths,
+ * unique shell quartets evaluated, model flops per primitive quartet, and -- only when the context was
+ * created with the environment variable QCF_PROFILE=1, which serialises the launches -- its device time.
+ * Returns the number of launches of the last build (writes at most max_rec records). */
+typedef struct {
+    int la, lb, kab, lc, ld, kcd, nbra, nket;
+    long long quartets;
+    double flops_per_prim_quartet;
+    float ms;
+} qcf_launch_rec;
+int qcf_launch_profile(qcf_ctx* ctx, int max_rec, qcf_launch_rec* out);
 const char* qcf_last_error(const qcf_ctx* ctx);
 void qcf_destroy(qcf_ctx* ctx);
 

@@ -7,10 +7,12 @@
 // There is no CPU fallback anywhere in this file: every failure of the CUDA runtime is reported.
 #include "../../include/qcfock.h"
 #include "eri_device.cuh"
+#include "onee.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -80,7 +82,7 @@ struct qcf_ctx {
     bool screening = true;
     // basis (host copies)
     int natoms = 0, nshell = 0, N = 0;
-    std::vector<double> xyz, exps, coefs;
+    std::vector<double> xyz, exps, coefs, charge;
     std::vector<int> sh_atom, sh_l, sh_np, sh_po, sh_off;
     std::vector<double> fscale;       // per basis function component scale
     std::vector<Group> groups;
@@ -101,8 +103,11 @@ struct qcf_ctx {
     cudaStream_t main_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     // stats of the last build
-    struct LaunchRec { int bra, ket; };
+    struct LaunchRec { int bra, ket; float ms = 0; };
+    bool profile = false;                 // QCF_PROFILE=1: serialise the class launches and time each one
+    std::vector<cudaEvent_t> prof_ev;
     std::vector<LaunchRec> launches;
+    std::vector<unsigned long long> launch_cnt;
     qcf_stats_t stats{};
     bool counters_pending = false;
 };
@@ -427,7 +432,12 @@ int run_build(qcf_ctx* ctx, int mode, const double* dPa, const double* dPb, doub
             if (nbra <= 0) continue;
             BuildArgs al = a;
             al.counter = ctx->d_counters + nl;
-            cl->jk(nk, nbra, ctx->block, ctx->streams[nl & 3], bra.dev, ket.dev, al, gi == gj ? 1 : 0);
+            if (ctx->profile) {
+                while ((int)ctx->prof_ev.size() < 2 * (nl + 1)) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
+                CK(cudaEventRecord(ctx->prof_ev[2 * nl], ctx->streams[0]));
+            }
+            cl->jk(nk, nbra, ctx->block, ctx->streams[ctx->profile ? 0 : (nl & 3)], bra.dev, ket.dev, al, gi == gj ? 1 : 0);
+            if (ctx->profile) CK(cudaEventRecord(ctx->prof_ev[2 * nl + 1], ctx->streams[0]));
             ctx->launches.push_back({gi, gj});
             ++nl;
         }
@@ -456,7 +466,9 @@ int collect_stats(qcf_ctx* ctx) {
     long long q = 0;
     double flops = 0;
     const double digest = 12.0;  // per unique contracted integral (RHF model)
+    ctx->launch_cnt.assign(cnt.begin(), cnt.begin() + nl);
     for (int i = 0; i < nl; ++i) {
+        if (ctx->profile) CK(cudaEventElapsedTime(&ctx->launches[i].ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
         const Group& b = ctx->groups[ctx->launches[i].bra];
         const Group& k = ctx->groups[ctx->launches[i].ket];
         q += (long long)cnt[i];
@@ -519,10 +531,13 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
         if (o->screen_tau < -0.5) ctx->screening = false;
         else if (o->screen_tau > 0) ctx->tau = o->screen_tau;
     }
+    if (const char* e = getenv("QCF_PROFILE")) ctx->profile = (e[0] == '1');
     if (ctx->rank < 0 || ctx->rank >= ctx->world) return fail(QCF_ERR_ARG, "rank outside [0, world_size)");
     if (ctx->block < 32 || ctx->block > 128 || ctx->block % 32) return fail(QCF_ERR_ARG, "block_threads must be 32, 64, 96 or 128");
     ctx->natoms = b->n_atoms; ctx->nshell = b->n_shells;
     ctx->xyz.assign(b->xyz, b->xyz + 3 * b->n_atoms);
+    ctx->charge.resize(b->n_atoms);
+    for (int i = 0; i < b->n_atoms; ++i) ctx->charge[i] = b->Z ? (double)b->Z[i] : 0.0;
     ctx->sh_atom.assign(b->shell_atom, b->shell_atom + b->n_shells);
     ctx->sh_l.assign(b->shell_l, b->shell_l + b->n_shells);
     ctx->sh_np.assign(b->shell_nprim, b->shell_nprim + b->n_shells);
@@ -685,6 +700,46 @@ int qcf_eri_quartet(qcf_ctx* ctx, int s1, int s2, int s3, int s4, double* out) {
     return QCF_OK;
 }
 
+int qcf_one_electron(qcf_ctx* ctx, double* S, double* T, double* V) {
+    if (!ctx || !S || !T || !V) return QCF_ERR_ARG;
+    if (!ctx->d_AJ) { ctx->err = "context was not created successfully"; return QCF_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    const size_t nn = (size_t)ctx->N * ctx->N;
+    int *d_i = nullptr;
+    double* d_d = nullptr;
+    const int ns = ctx->nshell, na = ctx->natoms;
+    std::vector<int> hi;
+    hi.insert(hi.end(), ctx->sh_atom.begin(), ctx->sh_atom.end());
+    hi.insert(hi.end(), ctx->sh_l.begin(), ctx->sh_l.end());
+    hi.insert(hi.end(), ctx->sh_np.begin(), ctx->sh_np.end());
+    hi.insert(hi.end(), ctx->sh_po.begin(), ctx->sh_po.end());
+    std::vector<double> hd;
+    hd.insert(hd.end(), ctx->exps.begin(), ctx->exps.end());
+    hd.insert(hd.end(), ctx->coefs.begin(), ctx->coefs.end());
+    hd.insert(hd.end(), ctx->xyz.begin(), ctx->xyz.end());
+    hd.insert(hd.end(), ctx->charge.begin(), ctx->charge.end());
+    CK(upload(&d_i, hi));
+    CK(upload(&d_d, hd));
+    double* d_out = nullptr;
+    CK(cudaMalloc(&d_out, 3 * nn * sizeof(double)));
+    CK(cudaMemset(d_out, 0, 3 * nn * sizeof(double)));
+    ShellData sd{};
+    sd.nshell = ns; sd.natoms = na; sd.N = ctx->N;
+    sd.atom = d_i; sd.l = d_i + ns; sd.nprim = d_i + 2 * ns; sd.prim_off = d_i + 3 * ns; sd.off = ctx->d_shoff;
+    const size_t npr = ctx->exps.size();
+    sd.exps = d_d; sd.coefs = d_d + npr; sd.xyz = d_d + 2 * npr; sd.charge = d_d + 2 * npr + 3 * (size_t)na;
+    sd.fscale = ctx->d_fscale;
+    const long long npair = (long long)ns * (ns + 1) / 2;
+    const long long nblk = (npair * 32 + 127) / 128;
+    onee_kernel<<<(unsigned)nblk, 128>>>(sd, ctx->d_boys, d_out, d_out + nn, d_out + 2 * nn);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(S, d_out, nn * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(T, d_out + nn, nn * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(V, d_out + 2 * nn, nn * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_out); cudaFree(d_i); cudaFree(d_d);
+    return QCF_OK;
+}
+
 int qcf_schwarz(qcf_ctx* ctx, double* Q) {
     if (!ctx || !Q) return QCF_ERR_ARG;
     const int ns = ctx->nshell;
@@ -745,6 +800,21 @@ int qcf_stats(const qcf_ctx* cctx, qcf_stats_t* out) {
     if (rc) return rc;
     *out = ctx->stats;
     return QCF_OK;
+}
+
+int qcf_launch_profile(qcf_ctx* ctx, int max_rec, qcf_launch_rec* out) {
+    if (!ctx || (max_rec > 0 && !out)) return QCF_ERR_ARG;
+    int rc = collect_stats(ctx);
+    if (rc) return rc;
+    const int nl = (int)ctx->launches.size();
+    for (int i = 0; i < nl && i < max_rec; ++i) {
+        const Group& b = ctx->groups[ctx->launches[i].bra];
+        const Group& k = ctx->groups[ctx->launches[i].ket];
+        out[i] = {b.la, b.lb, b.K, k.la, k.lb, k.K, b.dev.npair, k.dev.npair,
+                  i < (int)ctx->launch_cnt.size() ? (long long)ctx->launch_cnt[i] : 0,
+                  model_flops_prim(b.la, b.lb, k.la, k.lb), ctx->launches[i].ms};
+    }
+    return nl;
 }
 
 const char* qcf_last_error(const qcf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }

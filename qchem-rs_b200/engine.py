@@ -23,7 +23,7 @@ QCF_TAU_NONE = -1.0
 
 EXPORTS = ["qcf_create", "qcf_nbasis", "qcf_build_rhf", "qcf_build_uhf", "qcf_build_jk", "qcf_build_rhf_dev",
            "qcf_build_uhf_dev", "qcf_eri_quartet", "qcf_schwarz", "qcf_boys", "qcf_fp64_peak", "qcf_stats",
-           "qcf_last_error", "qcf_destroy"]
+           "qcf_launch_profile", "qcf_one_electron", "qcf_last_error", "qcf_destroy"]
 
 
 class FockError(RuntimeError):
@@ -40,6 +40,12 @@ class CStats(ctypes.Structure):
                 ("n_groups", ctypes.c_int), ("quartets", ctypes.c_longlong), ("quartets_total", ctypes.c_longlong),
                 ("model_flops", ctypes.c_double), ("kernel_ms", ctypes.c_double), ("total_ms", ctypes.c_double),
                 ("launches", ctypes.c_int)]
+
+
+class CLaunchRec(ctypes.Structure):
+    _fields_ = [("la", ctypes.c_int), ("lb", ctypes.c_int), ("kab", ctypes.c_int), ("lc", ctypes.c_int),
+                ("ld", ctypes.c_int), ("kcd", ctypes.c_int), ("nbra", ctypes.c_int), ("nket", ctypes.c_int),
+                ("quartets", ctypes.c_longlong), ("flops_per_prim_quartet", ctypes.c_double), ("ms", ctypes.c_float)]
 
 
 def build_library(force: bool = False, jobs: int = 8) -> Path:
@@ -68,9 +74,11 @@ def lib():
         L.qcf_build_uhf_dev.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5
         L.qcf_eri_quartet.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [_dp]
         L.qcf_schwarz.argtypes = [ctypes.c_void_p, _dp]
+        L.qcf_one_electron.argtypes = [ctypes.c_void_p, _dp, _dp, _dp]
         L.qcf_boys.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _dp, _dp]
         L.qcf_fp64_peak.argtypes = [ctypes.c_void_p, _dp]
         L.qcf_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(CStats)]
+        L.qcf_launch_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(CLaunchRec)]
         _LIB = L
     return _LIB
 
@@ -161,6 +169,12 @@ class FockEngine:
         self._check(self._lib.qcf_eri_quartet(self._ctx, int(a), int(b), int(c), int(d), _p(out)), "qcf_eri_quartet")
         return out
 
+    def one_electron(self):
+        """(S, T, V): molint::overlap / kinetic / nuclear (rhf.rs:41-43) evaluated on the device."""
+        S, T, V = (np.zeros((self.n, self.n)) for _ in range(3))
+        self._check(self._lib.qcf_one_electron(self._ctx, _p(S), _p(T), _p(V)), "qcf_one_electron")
+        return S, T, V
+
     def schwarz(self) -> np.ndarray:
         ns = len(self.fb.shell_l)
         Q = np.zeros((ns, ns))
@@ -177,6 +191,14 @@ class FockEngine:
         v = ctypes.c_double()
         self._check(self._lib.qcf_fp64_peak(self._ctx, ctypes.byref(v)), "qcf_fp64_peak")
         return v.value
+
+    def launch_profile(self) -> list:
+        n = self._lib.qcf_launch_profile(self._ctx, 0, None)
+        if n < 0:
+            self._check(n, "qcf_launch_profile")
+        recs = (CLaunchRec * max(n, 1))()
+        self._check(min(self._lib.qcf_launch_profile(self._ctx, n, recs), 0), "qcf_launch_profile")
+        return [{k: getattr(recs[i], k) for k, _ in CLaunchRec._fields_} for i in range(n)]
 
     def stats(self) -> dict:
         st = CStats()

@@ -280,3 +280,25 @@ def test_rhf_scf_parity_water_dimer_631gs():
     assert got.iterations == ref.iterations
     assert abs(got.total_energy() - ref.total_energy()) < E_TOL
     assert np.max(np.abs(got.fock - ref.fock)) < F_TOL
+
+
+@pytest.mark.parametrize("name", ["water_sto3g", "spd_random", "benzene_631g", "water3_631gs", "caffeine_631gs"])
+def test_one_electron_matrices_match_oracle(name):
+    """qcf_one_electron (stand-in for molint::overlap/kinetic/nuclear, rhf.rs:41-43) vs the oracle."""
+    if name == "water_sto3g":
+        system = load_system("water", "STO-3G")
+    elif name == "spd_random":
+        system = spd_random_system()[0]
+    elif name == "benzene_631g":
+        system = load_system("benzene", "6-31G")
+    elif name == "caffeine_631gs":
+        system = load_system("caffeine", "6-31G_st")
+    else:
+        system = water_cluster(3)
+    fb = system.flat()
+    S0, T0, V0 = oracle_lib.one_electron(fb)
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        S, T, V = eng.one_electron()
+    np.testing.assert_allclose(S, S0, atol=1e-12, rtol=1e-12)
+    np.testing.assert_allclose(T, T0, atol=1e-11, rtol=1e-12)
+    np.testing.assert_allclose(V, V0, atol=1e-10, rtol=1e-12)
