@@ -77,7 +77,7 @@ struct Group {
 
 struct qcf_ctx {
     std::string err;
-    int device = 0, rank = 0, world = 1, block = 64;
+    int device = 0, rank = 0, world = 1, block = 64, kets_per_thread = 4;
     double tau = 1e-12;
     bool screening = true;
     // basis (host copies)
@@ -432,11 +432,12 @@ int run_build(qcf_ctx* ctx, int mode, const double* dPa, const double* dPb, doub
             if (nbra <= 0) continue;
             BuildArgs al = a;
             al.counter = ctx->d_counters + nl;
+            const int nket_max = gi == gj ? bra.dev.npair : ket.dev.npair;
             if (ctx->profile) {
                 while ((int)ctx->prof_ev.size() < 2 * (nl + 1)) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
                 CK(cudaEventRecord(ctx->prof_ev[2 * nl], ctx->streams[0]));
             }
-            cl->jk(nk, nbra, ctx->block, ctx->streams[ctx->profile ? 0 : (nl & 3)], bra.dev, ket.dev, al, gi == gj ? 1 : 0);
+            cl->jk(nk, nbra, nket_max, ctx->block, ctx->kets_per_thread, ctx->streams[ctx->profile ? 0 : (nl & 3)], bra.dev, ket.dev, al, gi == gj ? 1 : 0);
             if (ctx->profile) CK(cudaEventRecord(ctx->prof_ev[2 * nl + 1], ctx->streams[0]));
             ctx->launches.push_back({gi, gj});
             ++nl;
@@ -532,6 +533,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
         else if (o->screen_tau > 0) ctx->tau = o->screen_tau;
     }
     if (const char* e = getenv("QCF_PROFILE")) ctx->profile = (e[0] == '1');
+    if (const char* e = getenv("QCF_KETS_PER_THREAD")) ctx->kets_per_thread = std::max(1, atoi(e));
     if (ctx->rank < 0 || ctx->rank >= ctx->world) return fail(QCF_ERR_ARG, "rank outside [0, world_size)");
     if (ctx->block < 32 || ctx->block > 128 || ctx->block % 32) return fail(QCF_ERR_ARG, "block_threads must be 32, 64, 96 or 128");
     ctx->natoms = b->n_atoms; ctx->nshell = b->n_shells;

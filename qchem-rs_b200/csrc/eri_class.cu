@@ -1,6 +1,7 @@
 // eri_class.cu -- one translation unit per angular class (LA LB | LC LD), compiled 21 times with
 // -DQCF_LA= -DQCF_LB= -DQCF_LC= -DQCF_LD= so that the classes build in parallel.
 #include "eri_device.cuh"
+#include "eri_slab.cuh"
 
 #ifndef QCF_LA
 #error "compile with -DQCF_LA=.. -DQCF_LB=.. -DQCF_LC=.. -DQCF_LD=.."
@@ -9,10 +10,51 @@
 namespace qcf {
 namespace {
 constexpr int LA = QCF_LA, LB = QCF_LB, LC = QCF_LC, LD = QCF_LD;
+constexpr int LTOT = LA + LB + LC + LD;
+constexpr int NCD = ncart(LC) * ncart(LD);
 
-void launch_jk(int nk, int grid, int block, cudaStream_t s, const PairGroup& bra, const PairGroup& ket, const BuildArgs& a, int same) {
-    if (nk == 1) eri_jk_kernel<LA, LB, LC, LD, 1><<<grid, block, 0, s>>>(bra, ket, a, same);
-    else eri_jk_kernel<LA, LB, LC, LD, 2><<<grid, block, 0, s>>>(bra, ket, a, same);
+// Which kernel serves this class, and how many ket components one thread of the slab kernel takes.
+// Slab kernel: every class with a dp or dd bra whose R_tuv still fits the register file (L <= 6).
+#ifdef QCF_SPT
+constexpr int SPT = QCF_SPT;
+#else
+constexpr int SPT = (LA == 2 && LB == 1 && LC == 1 && LD == 0) ? 3 : (LA == 2 && LB == 1 && LC == 2 && LD == 0) ? 2 : 1;
+#endif
+#ifdef QCF_USE_SLAB
+constexpr bool USE_SLAB = QCF_USE_SLAB;
+#else
+constexpr bool USE_SLAB = (LA == 2 && LB >= 1 && LTOT <= 6 && NCD / SPT <= 9);
+#endif
+
+template <int NK>
+void launch_slab(int nbra, int nket_max, int kpt, cudaStream_t s, const PairGroup& bra, const PairGroup& ket, BuildArgs a, int same) {
+    if constexpr (USE_SLAB) {
+        using C = SlabCfg<LA, LB, LC, LD, NK, SPT>;
+        auto kern = eri_jk_slab_kernel<LA, LB, LC, LD, NK, SPT>;
+        const size_t smem = slab_smem_bytes<LA, LB, LC, LD, NK, SPT>(bra.K);
+        static size_t smem_set = 0;
+        if (smem > smem_set) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            smem_set = smem;
+        }
+        a.ket_chunk = 32 * C::NSUB * kpt;
+        const dim3 grid(nbra, (nket_max + a.ket_chunk - 1) / a.ket_chunk);
+        kern<<<grid, C::BLOCK, smem, s>>>(bra, ket, a, same);
+    }
+}
+
+void launch_jk(int nk, int nbra, int nket_max, int block, int kpt, cudaStream_t s, const PairGroup& bra, const PairGroup& ket,
+               const BuildArgs& a0, int same) {
+    BuildArgs a = a0;
+    if constexpr (USE_SLAB) {
+        if (nk == 1) launch_slab<1>(nbra, nket_max, kpt, s, bra, ket, a, same);
+        else launch_slab<2>(nbra, nket_max, kpt, s, bra, ket, a, same);
+    } else {
+        a.ket_chunk = block * kpt;
+        const dim3 grid(nbra, (nket_max + a.ket_chunk - 1) / a.ket_chunk);
+        if (nk == 1) eri_jk_kernel<LA, LB, LC, LD, 1><<<grid, block, 0, s>>>(bra, ket, a, same);
+        else eri_jk_kernel<LA, LB, LC, LD, 2><<<grid, block, 0, s>>>(bra, ket, a, same);
+    }
 }
 void launch_quartet(cudaStream_t s, const PairGroup& bra, int ib_, const PairGroup& ket, int ik_, const double* boys, double* out) {
     quartet_kernel<LA, LB, LC, LD><<<1, 32, 0, s>>>(bra, ib_, ket, ik_, boys, out);

@@ -64,6 +64,7 @@ struct BuildArgs {
     unsigned long long* counter;  // evaluated quartets of this launch
     const double* boys;       // [BOYS_LTOT+1][BOYS_NGRID][BOYS_ROW]
     int rank, world;
+    int ket_chunk;            // kets per CTA (grid.y strides over the ket list)
 };
 
 // ---- Boys function -----------------------------------------------------------------------------
@@ -480,7 +481,9 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
         nket = lo;
     }
     if (same_group && nket > ib_ + 1) nket = ib_ + 1;
-    if (nket <= 0) return;
+    const int ket0 = blockIdx.y * a.ket_chunk;
+    if (nket <= ket0) return;
+    if (nket > ket0 + a.ket_chunk) nket = ket0 + a.ket_chunk;
 
     const int N = a.N;
     const int fa = __ldg(bra.fa + ib_), fb = __ldg(bra.fb + ib_);
@@ -494,7 +497,7 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     for (int i = 0; i < NAB; ++i) { jab[i] = 0.0; pab[i] = __ldg(a.Pj + (size_t)(fa + i / NB) * N + fb + i % NB); }
     unsigned int nq = 0;
 
-    for (int ik_ = threadIdx.x; ik_ < nket; ik_ += blockDim.x) {
+    for (int ik_ = ket0 + threadIdx.x; ik_ < nket; ik_ += blockDim.x) {
         const double qcd = __ldg(ket.Q + ik_);
         const int sc = __ldg(ket.sa + ik_), sd = __ldg(ket.sb + ik_);
         if (a.tau > 0.0) {
@@ -590,7 +593,7 @@ __global__ void quartet_kernel(PairGroup bra, int ib_, PairGroup ket, int ik_, c
 
 // ---- launch interface of one angular class (defined in eri_class.cu, one object per class) ------
 struct ClassLaunch {
-    void (*jk)(int nk, int grid, int block, cudaStream_t s, const PairGroup& bra, const PairGroup& ket, const BuildArgs& a, int same);
+    void (*jk)(int nk, int nbra, int nket_max, int block, int kets_per_thread, cudaStream_t s, const PairGroup& bra, const PairGroup& ket, const BuildArgs& a, int same);
     void (*quartet)(cudaStream_t s, const PairGroup& bra, int ib_, const PairGroup& ket, int ik_, const double* boys, double* out);
     void (*schwarz)(int grid, int block, cudaStream_t s, const PairGroup& g, const double* boys, double* Q);  // null unless (LA,LB)==(LC,LD)
 };

@@ -32,6 +32,6 @@ with engine.FockEngine(system, tau=1e-12) as eng:
     for k, v in sorted(agg.items(), key=lambda x: -x[1][0]):
         print(f"{k}  {v[0]:8.2f} {100*v[0]/tot:5.1f} {v[1]:.3e} {v[2]/max(v[0],1e-9)/1e9:7.3f}")
     print("top launches")
-    for r in sorted(recs, key=lambda r: -r['ms'])[:40]:
+    for r in sorted(recs, key=lambda r: -r["ms"])[:int(os.environ.get("TOPN", "40"))]:
         fl = r['quartets'] * (r['kab'] * r['kcd'] * r['flops_per_prim_quartet'])
         print(f"({r['la']}{r['lb']}|{r['lc']}{r['ld']}) K={r['kab']:2d}x{r['kcd']:2d} nbra={r['nbra']:6d} nket={r['nket']:6d} q={r['quartets']:.3e} ms={r['ms']:8.3f} TF={fl/max(r['ms'],1e-9)/1e9:7.3f} ns/q={1e6*r['ms']/max(r['quartets'],1):.2f}")
