@@ -69,7 +69,7 @@ struct Group {
     std::vector<HostPair> pairs;
     // device
     int* d_fa = nullptr; int* d_fb = nullptr; int* d_sa = nullptr; int* d_sb = nullptr;
-    double* d_Q = nullptr; double* d_prim = nullptr; double* d_AB = nullptr;
+    double* d_Q = nullptr; double* d_Qb = nullptr; double* d_prim = nullptr; double* d_AB = nullptr;
     PairGroup dev{};
 };
 
@@ -244,18 +244,22 @@ __global__ void fp64_peak_kernel(double* out, int iters, double x) {
 // ---- pair construction -------------------------------------------------------------------------------
 struct PairArrays {
     std::vector<int> fa, fb, sa, sb;
-    std::vector<double> Q, prim, AB;
+    std::vector<double> Q, Qb, prim, AB;
 };
+
+// power-of-two ceiling of a Schwarz factor: Q <= 2^ceil(log2 Q)
+inline int q_bucket(double Q) { return Q > 0 ? (int)std::ceil(std::log2(Q)) : -100000; }
+inline double q_bucket_ceiling(double Q) { return Q > 0 ? std::ldexp(1.0, q_bucket(Q)) : 0.0; }
 
 void fill_pair_arrays(const qcf_ctx* c, const Group& g, PairArrays& out) {
     const size_t np = g.pairs.size();
-    out.fa.resize(np); out.fb.resize(np); out.sa.resize(np); out.sb.resize(np); out.Q.resize(np);
+    out.fa.resize(np); out.fb.resize(np); out.sa.resize(np); out.sb.resize(np); out.Q.resize(np); out.Qb.resize(np);
     out.prim.assign((size_t)g.K * PF_COUNT * np, 0.0);
     out.AB.assign(3 * np, 0.0);
     const double cpi = std::sqrt(2.0) * std::pow(PI_D, 1.25);
     for (size_t i = 0; i < np; ++i) {
         const int sa = g.pairs[i].sa, sb = g.pairs[i].sb;
-        out.fa[i] = c->sh_off[sa]; out.fb[i] = c->sh_off[sb]; out.sa[i] = sa; out.sb[i] = sb; out.Q[i] = g.pairs[i].Q;
+        out.fa[i] = c->sh_off[sa]; out.fb[i] = c->sh_off[sb]; out.sa[i] = sa; out.sb[i] = sb; out.Q[i] = g.pairs[i].Q; out.Qb[i] = q_bucket_ceiling(g.pairs[i].Q);
         const double* A = &c->xyz[3 * c->sh_atom[sa]];
         const double* B = &c->xyz[3 * c->sh_atom[sb]];
         double AB2 = 0;
@@ -287,8 +291,8 @@ cudaError_t upload(T** dptr, const std::vector<T>& h) {
 }
 
 void free_group(Group& g) {
-    cudaFree(g.d_fa); cudaFree(g.d_fb); cudaFree(g.d_sa); cudaFree(g.d_sb); cudaFree(g.d_Q); cudaFree(g.d_prim); cudaFree(g.d_AB);
-    g.d_fa = g.d_fb = g.d_sa = g.d_sb = nullptr; g.d_Q = g.d_prim = g.d_AB = nullptr;
+    cudaFree(g.d_fa); cudaFree(g.d_fb); cudaFree(g.d_sa); cudaFree(g.d_sb); cudaFree(g.d_Q); cudaFree(g.d_Qb); cudaFree(g.d_prim); cudaFree(g.d_AB);
+    g.d_fa = g.d_fb = g.d_sa = g.d_sb = nullptr; g.d_Q = g.d_Qb = g.d_prim = g.d_AB = nullptr;
 }
 
 int upload_group(qcf_ctx* ctx, Group& g) {
@@ -296,9 +300,9 @@ int upload_group(qcf_ctx* ctx, Group& g) {
     fill_pair_arrays(ctx, g, pa);
     free_group(g);
     CK(upload(&g.d_fa, pa.fa)); CK(upload(&g.d_fb, pa.fb)); CK(upload(&g.d_sa, pa.sa)); CK(upload(&g.d_sb, pa.sb));
-    CK(upload(&g.d_Q, pa.Q)); CK(upload(&g.d_prim, pa.prim)); CK(upload(&g.d_AB, pa.AB));
+    CK(upload(&g.d_Q, pa.Q)); CK(upload(&g.d_Qb, pa.Qb)); CK(upload(&g.d_prim, pa.prim)); CK(upload(&g.d_AB, pa.AB));
     g.dev.npair = (int)g.pairs.size(); g.dev.K = g.K; g.dev.la = g.la; g.dev.lb = g.lb;
-    g.dev.fa = g.d_fa; g.dev.fb = g.d_fb; g.dev.sa = g.d_sa; g.dev.sb = g.d_sb; g.dev.Q = g.d_Q; g.dev.prim = g.d_prim; g.dev.AB = g.d_AB;
+    g.dev.fa = g.d_fa; g.dev.fb = g.d_fb; g.dev.sa = g.d_sa; g.dev.sb = g.d_sb; g.dev.Q = g.d_Q; g.dev.Qb = g.d_Qb; g.dev.prim = g.d_prim; g.dev.AB = g.d_AB;
     return QCF_OK;
 }
 
@@ -364,7 +368,11 @@ int build_pairs(qcf_ctx* ctx) {
             const double cut = ctx->tau * 1e-2 / std::max(ctx->qmax, 1e-300);
             g.pairs.erase(std::remove_if(g.pairs.begin(), g.pairs.end(), [&](const HostPair& p) { return p.Q < cut; }), g.pairs.end());
         }
-        std::stable_sort(g.pairs.begin(), g.pairs.end(), [](const HostPair& x, const HostPair& y) { return x.Q > y.Q; });
+        std::stable_sort(g.pairs.begin(), g.pairs.end(), [](const HostPair& x, const HostPair& y) {
+            const int bx = q_bucket(x.Q), by = q_bucket(y.Q);
+            if (bx != by) return bx > by;
+            return x.sa != y.sa ? x.sa < y.sa : x.sb < y.sb;
+        });
         npairs += g.pairs.size();
     }
     ctx->groups.erase(std::remove_if(ctx->groups.begin(), ctx->groups.end(), [](const Group& g) { return g.pairs.empty(); }),
@@ -426,7 +434,7 @@ int run_build(qcf_ctx* ctx, int mode, const double* dPa, const double* dPb, doub
         for (int gj = gi; gj >= 0; --gj) {
             const Group& bra = ctx->groups[gi];
             const Group& ket = ctx->groups[gj];
-            if (a.tau > 0.0 && bra.pairs[0].Q * ket.pairs[0].Q * a.dmax < a.tau) continue;
+            if (a.tau > 0.0 && q_bucket_ceiling(bra.pairs[0].Q) * q_bucket_ceiling(ket.pairs[0].Q) * a.dmax < a.tau) continue;
             const ClassLaunch* cl = class_table(bra.cls, ket.cls);
             const int nbra = (bra.dev.npair - ctx->rank + ctx->world - 1) / ctx->world;
             if (nbra <= 0) continue;

@@ -18,12 +18,24 @@ constexpr int NCD = ncart(LC) * ncart(LD);
 #ifdef QCF_SPT
 constexpr int SPT = QCF_SPT;
 #else
-constexpr int SPT = (LA == 2 && LB == 1 && LC == 1 && LD == 0) ? 3 : (LA == 2 && LB == 1 && LC == 2 && LD == 0) ? 2 : 1;
+// largest divisor of NCD whose register-resident state (Hsum + R_tuv, or Hsum + digestion state) stays near 100 doubles
+constexpr int choose_spt() {
+    const int nh = nherm(LA + LB), nr = nherm(LTOT), nb = ncart(LB), nab = ncart(LA) * ncart(LB);
+    int best = 1;
+    for (int s = 1; s <= NCD; ++s) {
+        if (NCD % s) continue;
+        const int digest = s * 4 * (nb + 1) + (nab > 18 ? 0 : nab);
+        const int live = s * nh + (nr > digest ? nr : digest);
+        if (live <= 128) best = s;
+    }
+    return best;
+}
+constexpr int SPT = choose_spt();
 #endif
 #ifdef QCF_USE_SLAB
 constexpr bool USE_SLAB = QCF_USE_SLAB;
 #else
-constexpr bool USE_SLAB = (LA == 2 && LB >= 1 && LTOT <= 6 && NCD / SPT <= 9);
+constexpr bool USE_SLAB = (LA == 2 && LB >= 1) && LTOT <= 7;   // (dd|dd): R_tuv (165 values) cannot stay in registers; served by the block kernel
 #endif
 
 template <int NK>
@@ -38,7 +50,7 @@ void launch_slab(int nbra, int nket_max, int kpt, cudaStream_t s, const PairGrou
             smem_set = smem;
         }
         a.ket_chunk = 32 * C::NSUB * kpt;
-        const dim3 grid(nbra, (nket_max + a.ket_chunk - 1) / a.ket_chunk);
+        const dim3 grid(nbra, (nket_max + a.ket_chunk - 1) / a.ket_chunk, C::G);
         kern<<<grid, C::BLOCK, smem, s>>>(bra, ket, a, same);
     }
 }

@@ -36,7 +36,8 @@ __host__ __device__ constexpr int hidx(int t, int u, int v) {
 
 // ---- pair data layout --------------------------------------------------------------------------
 // One "pair group" = all significant shell pairs of one (la >= lb) class with the same number of
-// primitive pairs K, sorted by Schwarz bound (descending).  Structure of arrays: field f of primitive
+// primitive pairs K, sorted by power-of-two Schwarz bucket (descending) and, inside a bucket, by shell
+// indices, so that neighbouring lanes gather/scatter neighbouring density and Fock elements.  Structure of arrays: field f of primitive
 // k of pair i sits at prim[(k * PF_COUNT + f) * npair + i], so consecutive kets (= consecutive lanes)
 // read consecutive doubles.
 enum PrimField { PF_P = 0, PF_PX, PF_PY, PF_PZ, PF_C, PF_PAX, PF_PAY, PF_PAZ, PF_COUNT };
@@ -46,7 +47,8 @@ struct PairGroup {
     const int* fb;
     const int* sa;        // shell ids (density-block screening)
     const int* sb;
-    const double* Q;      // Schwarz factor, descending
+    const double* Q;      // Schwarz factor
+    const double* Qb;     // power-of-two bucket ceiling of Q, non-increasing along the list (prefix search)
     const double* prim;   // [K][PF_COUNT][npair];  PF_C = sqrt(2) pi^(5/4) c_a c_b exp(-mu AB^2) / p
     const double* AB;     // [3][npair]  A - B
 };
@@ -477,7 +479,7 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     if (a.tau > 0.0) {
         const double need = a.tau / (qab * a.dmax);
         int lo = 0, hi = ket.npair;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(ket.Q + mid) >= need) lo = mid + 1; else hi = mid; }
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(ket.Qb + mid) >= need) lo = mid + 1; else hi = mid; }
         nket = lo;
     }
     if (same_group && nket > ib_ + 1) nket = ib_ + 1;

@@ -6,8 +6,8 @@
 //   * one CTA = one bra pair x one chunk of the ket list.  Everything that depends on the bra pair only --
 //     primitive data and the combined Hermite coefficients E3[ab][tuv] = Ex_t Ey_u Ez_v -- is built once per
 //     CTA in shared memory and then read as warp-uniform (broadcast) operands;
-//   * one thread = one ket pair x one group of SPT ket components ("slabs"); the slab group is warp-uniform,
-//     so each warp runs straight-line code specialised for its ket components with every index a compile-time
+//   * one thread = one ket pair x one group of SPT ket components ("slabs"); the slab group is CTA-uniform
+//     (grid.z), so each CTA runs straight-line code specialised for its ket components with every index a compile-time
 //     constant (R_tuv, the ket-contracted Hermite integrals Hsum and the accumulators stay in registers);
 //   * the ket primitives are contracted at the Hermite level, Hsum[tuv] = sum_kc sum_q E^cd_q R_{tuv+q}, so the
 //     bra transform and the digestion run once per (quartet, bra primitive), never per primitive quartet;
@@ -42,9 +42,9 @@ struct SlabCfg {
     static constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
     static constexpr int NAB = NA * NB, NCD = NC * ND;
     static_assert(NCD % SPT == 0, "slabs per thread must divide the number of ket components");
-    static constexpr int G = NCD / SPT;                                // slab groups (one per warp role)
-    static constexpr int NSUB = G >= 4 ? 1 : (G == 3 ? 1 : (G == 2 ? 2 : 4));   // ket sub-chunks per CTA
-    static constexpr int BLOCK = 32 * G * NSUB;
+    static constexpr int G = NCD / SPT;                                // slab groups (grid.z; CTA-uniform)
+    static constexpr int NSUB = 4;                                     // warps per CTA, each 32 kets per pass
+    static constexpr int BLOCK = 32 * NSUB;
     static constexpr bool JSMEM = NAB > 18;                            // J_ab accumulators in shared memory
     static constexpr int LAB = LA + LB, L = LA + LB + LC + LD;
     static constexpr int NH = nherm(LAB);
@@ -232,7 +232,7 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     if (a.tau > 0.0) {
         const double need = a.tau / (qab * a.dmax);
         int lo = 0, hi = ket.npair;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(ket.Q + mid) >= need) lo = mid + 1; else hi = mid; }
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(ket.Qb + mid) >= need) lo = mid + 1; else hi = mid; }
         nket = lo;
     }
     if (same_group && nket > ib_ + 1) nket = ib_ + 1;
@@ -303,7 +303,7 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sg = warp % G, ksub = warp / G;
+    const int sg = blockIdx.z, ksub = warp;
     double* const jab_s = jab_all + threadIdx.x;
 
     double jab[NAB];
