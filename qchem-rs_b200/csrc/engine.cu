@@ -77,7 +77,7 @@ struct Group {
 
 struct qcf_ctx {
     std::string err;
-    int device = 0, rank = 0, world = 1, block = 64, kets_per_thread = 4;
+    int device = 0, rank = 0, world = 1, block = 64, kets_per_thread = 8, target_ctas = 148 * 16;
     double tau = 1e-12;
     bool screening = true;
     // basis (host copies)
@@ -149,6 +149,7 @@ std::vector<double> make_boys_table() {
                 if (k > 0) fact *= k;
                 tab[((size_t)L * BOYS_NGRID + g) * BOYS_ROW + k] = (double)(F[L + k] / fact);
             }
+            tab[((size_t)L * BOYS_NGRID + g) * BOYS_ROW + BOYS_ORDER + 1] = (double)e;
         }
     }
     return tab;
@@ -441,11 +442,19 @@ int run_build(qcf_ctx* ctx, int mode, const double* dPa, const double* dPb, doub
             BuildArgs al = a;
             al.counter = ctx->d_counters + nl;
             const int nket_max = gi == gj ? bra.dev.npair : ket.dev.npair;
+            // kets per thread: long lists amortise the per-CTA prologue / J_ab reduction over many kets, short
+            // lists are cut finer so that the grid still fills the 148 SMs (matters for the d-bra classes and
+            // for the per-rank share of a multi-GPU run)
+            const bool slab = bra.la == 2 && bra.lb >= 1 && bra.la + bra.lb + ket.la + ket.lb <= 7;
+            const int cta_threads = slab ? 128 : ctx->block;
+            const long long want_chunks = (ctx->target_ctas + nbra - 1) / nbra;
+            int kpt = (int)(nket_max / (want_chunks * cta_threads));
+            kpt = std::max(1, std::min(kpt, ctx->kets_per_thread));
             if (ctx->profile) {
                 while ((int)ctx->prof_ev.size() < 2 * (nl + 1)) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
                 CK(cudaEventRecord(ctx->prof_ev[2 * nl], ctx->streams[0]));
             }
-            cl->jk(nk, nbra, nket_max, ctx->block, ctx->kets_per_thread, ctx->streams[ctx->profile ? 0 : (nl & 3)], bra.dev, ket.dev, al, gi == gj ? 1 : 0);
+            cl->jk(nk, nbra, nket_max, ctx->block, kpt, ctx->streams[ctx->profile ? 0 : (nl & 3)], bra.dev, ket.dev, al, gi == gj ? 1 : 0);
             if (ctx->profile) CK(cudaEventRecord(ctx->prof_ev[2 * nl + 1], ctx->streams[0]));
             ctx->launches.push_back({gi, gj});
             ++nl;
@@ -542,6 +551,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     }
     if (const char* e = getenv("QCF_PROFILE")) ctx->profile = (e[0] == '1');
     if (const char* e = getenv("QCF_KETS_PER_THREAD")) ctx->kets_per_thread = std::max(1, atoi(e));
+    if (const char* e = getenv("QCF_TARGET_CTAS")) ctx->target_ctas = std::max(1, atoi(e));
     if (ctx->rank < 0 || ctx->rank >= ctx->world) return fail(QCF_ERR_ARG, "rank outside [0, world_size)");
     if (ctx->block < 32 || ctx->block > 128 || ctx->block % 32) return fail(QCF_ERR_ARG, "block_threads must be 32, 64, 96 or 128");
     ctx->natoms = b->n_atoms; ctx->nshell = b->n_shells;

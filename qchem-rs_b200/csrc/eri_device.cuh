@@ -19,7 +19,7 @@ constexpr double BOYS_TMAX = 36.0;
 constexpr int BOYS_PER_UNIT = 16;            // grid step 1/16
 constexpr int BOYS_NGRID = 36 * BOYS_PER_UNIT + 1;
 constexpr int BOYS_ORDER = 6;                // Taylor order (7 terms), |dT| <= 1/32 -> 6e-15
-constexpr int BOYS_ROW = 8;                  // doubles per grid point and class
+constexpr int BOYS_ROW = 8;                  // doubles per grid point and class: 7 Taylor coefficients + exp(-T0)
 
 // ---- compile-time index helpers ---------------------------------------------------------------
 __host__ __device__ constexpr int ncart(int l) { return (l + 1) * (l + 2) / 2; }
@@ -69,6 +69,24 @@ struct BuildArgs {
     int ket_chunk;            // kets per CTA (grid.y strides over the ket list)
 };
 
+// ---- fast reciprocal square root / reciprocal (positive, normal arguments) --------------------------
+// IEEE division and sqrt cost 20-40 instructions each in FP64 and were two thirds of all instructions
+// executed by the (ss|ss) and (ps|ss) kernels.  MUFU.RSQ64H seed (2^-22) + two Newton steps: <= 2 ulp.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    return y;
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+    const double r = fast_rsqrt(x);
+    return r * r;
+}
+
 // ---- Boys function -----------------------------------------------------------------------------
 // F_0..F_L(T).  T < 36: 7-term Taylor expansion of F_L about the nearest grid point (table row holds
 // F_{L+k}(T0)/k!), then the stable downward recursion F_{m-1} = (2T F_m + e^-T)/(2m-1).  T >= 36:
@@ -84,14 +102,20 @@ __device__ __forceinline__ void boys(double T, const double* __restrict__ table,
         for (int k = 5; k >= 0; --k) f = fma(f, d, __ldg(r + k));
         F[L] = f;
         if constexpr (L > 0) {
-            const double e = exp(-T);
+            // exp(-T) = exp(-T0) exp(d), |d| <= 1/32: row slot 7 holds exp(-T0); 8-term Taylor (< 1e-19)
+            double ed = 1.0 / 40320.0;
+            ed = fma(ed, d, 1.0 / 5040.0); ed = fma(ed, d, 1.0 / 720.0); ed = fma(ed, d, 1.0 / 120.0);
+            ed = fma(ed, d, 1.0 / 24.0); ed = fma(ed, d, 1.0 / 6.0); ed = fma(ed, d, 0.5);
+            ed = fma(ed, d, 1.0); ed = fma(ed, d, 1.0);
+            const double e = __ldg(r + 7) * ed;
             const double t2 = 2.0 * T;
 #pragma unroll
             for (int m = L; m > 0; --m) F[m - 1] = fma(t2, F[m], e) * (1.0 / (2 * m - 1));
         }
     } else {
-        const double rt = 1.0 / T;
-        F[0] = 0.5 * sqrt(PI_D * rt);
+        const double rs = fast_rsqrt(T);
+        const double rt = rs * rs;
+        F[0] = 0.88622692545275801365 * rs;       // sqrt(pi)/2 / sqrt(T)
         if constexpr (L > 0) {
             const double e = exp(-T);
             const double h = 0.5 * rt;
@@ -280,14 +304,15 @@ __device__ __forceinline__ void prim_quartet(const PairE<LA, LB>& Eab, const Pai
     constexpr bool CUBE = ClassTraits<LA, LB, LC, LD>::LARGE;
     constexpr int NC = ncart(LC), ND = ncart(LD);
     const double pq = p + q;
-    const double rpq = 1.0 / pq;
+    const double rspq = fast_rsqrt(pq);
+    const double rpq = rspq * rspq;
     const double alpha = p * q * rpq;
     const double T = alpha * (PQx * PQx + PQy * PQy + PQz * PQz);
     double F[L + 1];
     boys<L>(T, boys_table, F);
     double c[L + 1];
     {
-        double f = cPcQ * sqrt(rpq);
+        double f = cPcQ * rspq;
         const double m2a = -2.0 * alpha;
 #pragma unroll
         for (int n = 0; n <= L; ++n) { c[n] = f * F[n]; f *= m2a; }
@@ -320,7 +345,7 @@ __device__ __forceinline__ void load_prim(const PairGroup& g, int i, int k, doub
     Pz = __ldg(base + PF_PZ * np);
     cP = __ldg(base + PF_C * np);
     if constexpr (LA + LB > 0) {
-        const double h = 0.5 / p;
+        const double h = 0.5 * fast_rcp(p);
         const double pax = __ldg(base + PF_PAX * np), pay = __ldg(base + PF_PAY * np), paz = __ldg(base + PF_PAZ * np);
         // P - B = (P - A) + (A - B)
         E.ax[0].build(h, pax, pax + ABx, ket_sign);

@@ -341,13 +341,13 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
                 double q, Qx, Qy, Qz, cQ;
                 PairE<LC, LD> Ecd;
                 load_prim<LC, LD>(ket, ik_, kc, CDx, CDy, CDz, q, Qx, Qy, Qz, cQ, Ecd, true);
-                const double pq = p + q, rpq = 1.0 / pq, alpha = p * q * rpq;
+                const double pq = p + q, rspq = fast_rsqrt(pq), rpq = rspq * rspq, alpha = p * q * rpq;
                 const double X = Px - Qx, Y = Py - Qy, Z = Pz - Qz;
                 double F[L + 1];
                 boys<L>(alpha * (X * X + Y * Y + Z * Z), a.boys, F);
                 double c[L + 1];
                 {
-                    double f = cP * cQ * sqrt(rpq);
+                    double f = cP * cQ * rspq;
                     const double m2a = -2.0 * alpha;
 #pragma unroll
                     for (int n = 0; n <= L; ++n) { c[n] = f * F[n]; f *= m2a; }
