@@ -66,6 +66,8 @@ typedef struct {
     double kernel_ms;          /* device time of the last build's kernels (CUDA events)           */
     double total_ms;           /* last build, including H2D / D2H copies                          */
     int launches;              /* kernels launched by the last build                              */
+    long long prim_pairs;      /* primitive pairs of all shell pairs before primitive screening    */
+    long long prim_pairs_kept; /* ... and those the kernels loop over                               */
 } qcf_stats_t;
 
 /* Build shell pairs, Schwarz bounds and the device-resident pair data.  (Replaces the one-off

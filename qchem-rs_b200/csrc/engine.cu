@@ -62,13 +62,15 @@ double model_flops_prim(int la, int lb, int lc, int ld) {
 struct HostPair {
     int sa, sb;       // shell ids, shell sa has l >= shell sb
     double Q;
+    int keff = -1;                      // primitive pairs kept (-1: all K)
+    std::vector<unsigned char> order;   // primitive-pair order (by primitive Schwarz factor); empty: natural
 };
 
 struct Group {
     int la, lb, K, cls;
     std::vector<HostPair> pairs;
     // device
-    int* d_fa = nullptr; int* d_fb = nullptr; int* d_sa = nullptr; int* d_sb = nullptr;
+    int* d_fa = nullptr; int* d_fb = nullptr; int* d_sa = nullptr; int* d_sb = nullptr; int* d_np = nullptr;
     double* d_Q = nullptr; double* d_Qb = nullptr; double* d_prim = nullptr; double* d_AB = nullptr;
     PairGroup dev{};
 };
@@ -88,6 +90,7 @@ struct qcf_ctx {
     std::vector<Group> groups;
     std::map<std::pair<int, int>, std::pair<int, int>> pair_index;  // (sa,sb) canonical -> (group, index)
     double qmax = 0;
+    long long prim_total = 0, prim_kept = 0;
     // device state
     double* d_boys = nullptr;
     double* d_fscale = nullptr;
@@ -99,9 +102,11 @@ struct qcf_ctx {
     unsigned long long* d_counters = nullptr;
     int max_launch = 0;
     double* h_pin = nullptr;  // pinned staging, 2*N*N
-    cudaStream_t streams[4] = {};
+    static constexpr int MAXSTREAM = 16;
+    int nstreams = 8;
+    cudaStream_t streams[MAXSTREAM] = {};
     cudaStream_t main_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join[4] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join[MAXSTREAM] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     // stats of the last build
     struct LaunchRec { int bra, ket; float ms = 0; };
     bool profile = false;                 // QCF_PROFILE=1: serialise the class launches and time each one
@@ -244,7 +249,7 @@ __global__ void fp64_peak_kernel(double* out, int iters, double x) {
 
 // ---- pair construction -------------------------------------------------------------------------------
 struct PairArrays {
-    std::vector<int> fa, fb, sa, sb;
+    std::vector<int> fa, fb, sa, sb, np;
     std::vector<double> Q, Qb, prim, AB;
 };
 
@@ -254,7 +259,7 @@ inline double q_bucket_ceiling(double Q) { return Q > 0 ? std::ldexp(1.0, q_buck
 
 void fill_pair_arrays(const qcf_ctx* c, const Group& g, PairArrays& out) {
     const size_t np = g.pairs.size();
-    out.fa.resize(np); out.fb.resize(np); out.sa.resize(np); out.sb.resize(np); out.Q.resize(np); out.Qb.resize(np);
+    out.fa.resize(np); out.fb.resize(np); out.sa.resize(np); out.sb.resize(np); out.Q.resize(np); out.Qb.resize(np); out.np.resize(np);
     out.prim.assign((size_t)g.K * PF_COUNT * np, 0.0);
     out.AB.assign(3 * np, 0.0);
     const double cpi = std::sqrt(2.0) * std::pow(PI_D, 1.25);
@@ -265,9 +270,12 @@ void fill_pair_arrays(const qcf_ctx* c, const Group& g, PairArrays& out) {
         const double* B = &c->xyz[3 * c->sh_atom[sb]];
         double AB2 = 0;
         for (int k = 0; k < 3; ++k) { out.AB[k * np + i] = A[k] - B[k]; AB2 += (A[k] - B[k]) * (A[k] - B[k]); }
-        int kk = 0;
-        for (int ia = 0; ia < c->sh_np[sa]; ++ia)
-            for (int ib = 0; ib < c->sh_np[sb]; ++ib, ++kk) {
+        out.np[i] = g.pairs[i].keff < 0 ? g.K : g.pairs[i].keff;
+        const int npb = c->sh_np[sb];
+        for (int kk = 0; kk < g.K; ++kk) {
+            {
+                const int ksel = g.pairs[i].order.empty() ? kk : g.pairs[i].order[kk];
+                const int ia = ksel / npb, ib = ksel % npb;
                 const double a = c->exps[c->sh_po[sa] + ia], b = c->exps[c->sh_po[sb] + ib];
                 const double ca = c->coefs[c->sh_po[sa] + ia], cb = c->coefs[c->sh_po[sb] + ib];
                 const double p = a + b, mu = a * b / p;
@@ -280,6 +288,7 @@ void fill_pair_arrays(const qcf_ctx* c, const Group& g, PairArrays& out) {
                 }
                 f[PF_C * np] = cpi * ca * cb * std::exp(-mu * AB2) / p;
             }
+        }
     }
 }
 
@@ -292,18 +301,18 @@ cudaError_t upload(T** dptr, const std::vector<T>& h) {
 }
 
 void free_group(Group& g) {
-    cudaFree(g.d_fa); cudaFree(g.d_fb); cudaFree(g.d_sa); cudaFree(g.d_sb); cudaFree(g.d_Q); cudaFree(g.d_Qb); cudaFree(g.d_prim); cudaFree(g.d_AB);
-    g.d_fa = g.d_fb = g.d_sa = g.d_sb = nullptr; g.d_Q = g.d_Qb = g.d_prim = g.d_AB = nullptr;
+    cudaFree(g.d_fa); cudaFree(g.d_fb); cudaFree(g.d_sa); cudaFree(g.d_sb); cudaFree(g.d_np); cudaFree(g.d_Q); cudaFree(g.d_Qb); cudaFree(g.d_prim); cudaFree(g.d_AB);
+    g.d_fa = g.d_fb = g.d_sa = g.d_sb = g.d_np = nullptr; g.d_Q = g.d_Qb = g.d_prim = g.d_AB = nullptr;
 }
 
 int upload_group(qcf_ctx* ctx, Group& g) {
     PairArrays pa;
     fill_pair_arrays(ctx, g, pa);
     free_group(g);
-    CK(upload(&g.d_fa, pa.fa)); CK(upload(&g.d_fb, pa.fb)); CK(upload(&g.d_sa, pa.sa)); CK(upload(&g.d_sb, pa.sb));
+    CK(upload(&g.d_fa, pa.fa)); CK(upload(&g.d_fb, pa.fb)); CK(upload(&g.d_sa, pa.sa)); CK(upload(&g.d_sb, pa.sb)); CK(upload(&g.d_np, pa.np));
     CK(upload(&g.d_Q, pa.Q)); CK(upload(&g.d_Qb, pa.Qb)); CK(upload(&g.d_prim, pa.prim)); CK(upload(&g.d_AB, pa.AB));
     g.dev.npair = (int)g.pairs.size(); g.dev.K = g.K; g.dev.la = g.la; g.dev.lb = g.lb;
-    g.dev.fa = g.d_fa; g.dev.fb = g.d_fb; g.dev.sa = g.d_sa; g.dev.sb = g.d_sb; g.dev.Q = g.d_Q; g.dev.Qb = g.d_Qb; g.dev.prim = g.d_prim; g.dev.AB = g.d_AB;
+    g.dev.fa = g.d_fa; g.dev.fb = g.d_fb; g.dev.sa = g.d_sa; g.dev.sb = g.d_sb; g.dev.nprim = g.d_np; g.dev.Q = g.d_Q; g.dev.Qb = g.d_Qb; g.dev.prim = g.d_prim; g.dev.AB = g.d_AB;
     return QCF_OK;
 }
 
@@ -362,6 +371,43 @@ int build_pairs(qcf_ctx* ctx) {
         cudaFree(dQ);
         for (int i = 0; i < np; ++i) { g.pairs[i].Q = Q[i]; ctx->qmax = std::max(ctx->qmax, Q[i]); }
     }
+    // primitive screening: Schwarz factor of every primitive pair on its own (the same class kernel on a
+    // K = 1 list); inside each shell pair the primitives are sorted by it and those that cannot contribute
+    // Q_k * Q_max >= 1e-4 tau to any integral are dropped (the kernels loop over nprim[i] <= K primitives)
+    ctx->prim_total = ctx->prim_kept = 0;
+    for (auto& g : ctx->groups) {
+        const long long np = (long long)g.pairs.size();
+        ctx->prim_total += np * g.K;
+        if (!ctx->screening || g.K == 1) { ctx->prim_kept += np * g.K; continue; }
+        Group g1; g1.la = g.la; g1.lb = g.lb; g1.K = 1; g1.cls = g.cls;
+        g1.pairs.reserve((size_t)np * g.K);
+        for (const auto& pr : g.pairs)
+            for (int k = 0; k < g.K; ++k) { HostPair h{pr.sa, pr.sb, 0.0}; h.order.assign(1, (unsigned char)k); g1.pairs.push_back(std::move(h)); }
+        // the K = 1 list holds primitive `order[0]` of each pair in slot 0
+        int rc = upload_group(ctx, g1);
+        if (rc) return rc;
+        const int n1 = (int)g1.pairs.size();
+        double* dQ = nullptr;
+        CK(cudaMalloc(&dQ, sizeof(double) * n1));
+        class_table(g.cls, g.cls)->schwarz((n1 + 63) / 64, 64, 0, g1.dev, ctx->d_boys, dQ);
+        CK(cudaGetLastError());
+        std::vector<double> Qk(n1);
+        CK(cudaMemcpy(Qk.data(), dQ, sizeof(double) * n1, cudaMemcpyDeviceToHost));
+        cudaFree(dQ);
+        free_group(g1);
+        const double pcut = ctx->tau * 1e-4 / std::max(ctx->qmax, 1e-300);
+        for (long long i = 0; i < np; ++i) {
+            auto& pr = g.pairs[i];
+            pr.order.resize(g.K);
+            for (int k = 0; k < g.K; ++k) pr.order[k] = (unsigned char)k;
+            const double* q = &Qk[(size_t)i * g.K];
+            std::stable_sort(pr.order.begin(), pr.order.end(), [&](unsigned char x, unsigned char y) { return q[x] > q[y]; });
+            int keep = 0;
+            while (keep < g.K && q[pr.order[keep]] >= pcut) ++keep;
+            pr.keff = std::max(keep, 1);
+            ctx->prim_kept += pr.keff;
+        }
+    }
     // drop negligible pairs, sort by Q, final upload
     size_t npairs = 0;
     for (auto& g : ctx->groups) {
@@ -386,6 +432,8 @@ int build_pairs(qcf_ctx* ctx) {
     }
     ctx->stats.n_pairs = (int)npairs;
     ctx->stats.n_groups = (int)ctx->groups.size();
+    ctx->stats.prim_pairs = ctx->prim_total;
+    ctx->stats.prim_pairs_kept = ctx->prim_kept;
     return QCF_OK;
 }
 
@@ -426,19 +474,30 @@ int run_build(qcf_ctx* ctx, int mode, const double* dPa, const double* dPb, doub
     a.rank = ctx->rank; a.world = ctx->world;
 
     CK(cudaEventRecord(ctx->ev_fork, ms));
-    for (int s = 0; s < 4; ++s) CK(cudaStreamWaitEvent(ctx->streams[s], ctx->ev_fork, 0));
+    for (int s = 0; s < ctx->nstreams; ++s) CK(cudaStreamWaitEvent(ctx->streams[s], ctx->ev_fork, 0));
     ctx->launches.clear();
     int nl = 0;
     const int ng = (int)ctx->groups.size();
-    // heavy classes first (largest angular momentum), so the tail is made of cheap kernels
+    // modelled-cost order, most expensive first, round-robin over the streams: the tail of the build is
+    // made of cheap kernels and every stream gets a similar share
+    struct Planned { int gi, gj; double cost; };
+    std::vector<Planned> plan;
     for (int gi = ng - 1; gi >= 0; --gi)
         for (int gj = gi; gj >= 0; --gj) {
             const Group& bra = ctx->groups[gi];
             const Group& ket = ctx->groups[gj];
             if (a.tau > 0.0 && q_bucket_ceiling(bra.pairs[0].Q) * q_bucket_ceiling(ket.pairs[0].Q) * a.dmax < a.tau) continue;
+            if ((bra.dev.npair - ctx->rank + ctx->world - 1) / ctx->world <= 0) continue;
+            const double nq = (double)bra.dev.npair * ket.dev.npair * (gi == gj ? 0.5 : 1.0);
+            plan.push_back({gi, gj, nq * ((double)bra.K * ket.K * model_flops_prim(bra.la, bra.lb, ket.la, ket.lb) + 400.0)});
+        }
+    std::stable_sort(plan.begin(), plan.end(), [](const Planned& x, const Planned& y) { return x.cost > y.cost; });
+    for (const Planned& pl : plan) {
+            const int gi = pl.gi, gj = pl.gj;
+            const Group& bra = ctx->groups[gi];
+            const Group& ket = ctx->groups[gj];
             const ClassLaunch* cl = class_table(bra.cls, ket.cls);
             const int nbra = (bra.dev.npair - ctx->rank + ctx->world - 1) / ctx->world;
-            if (nbra <= 0) continue;
             BuildArgs al = a;
             al.counter = ctx->d_counters + nl;
             const int nket_max = gi == gj ? bra.dev.npair : ket.dev.npair;
@@ -454,13 +513,13 @@ int run_build(qcf_ctx* ctx, int mode, const double* dPa, const double* dPb, doub
                 while ((int)ctx->prof_ev.size() < 2 * (nl + 1)) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
                 CK(cudaEventRecord(ctx->prof_ev[2 * nl], ctx->streams[0]));
             }
-            cl->jk(nk, nbra, nket_max, ctx->block, kpt, ctx->streams[ctx->profile ? 0 : (nl & 3)], bra.dev, ket.dev, al, gi == gj ? 1 : 0);
+            cl->jk(nk, nbra, nket_max, ctx->block, kpt, ctx->streams[ctx->profile ? 0 : (nl % ctx->nstreams)], bra.dev, ket.dev, al, gi == gj ? 1 : 0);
             if (ctx->profile) CK(cudaEventRecord(ctx->prof_ev[2 * nl + 1], ctx->streams[0]));
             ctx->launches.push_back({gi, gj});
             ++nl;
         }
     CK(cudaGetLastError());
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < ctx->nstreams; ++s) {
         CK(cudaEventRecord(ctx->ev_join[s], ctx->streams[s]));
         CK(cudaStreamWaitEvent(ms, ctx->ev_join[s], 0));
     }
@@ -551,6 +610,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     }
     if (const char* e = getenv("QCF_PROFILE")) ctx->profile = (e[0] == '1');
     if (const char* e = getenv("QCF_KETS_PER_THREAD")) ctx->kets_per_thread = std::max(1, atoi(e));
+    if (const char* e = getenv("QCF_STREAMS")) ctx->nstreams = std::min((int)qcf_ctx::MAXSTREAM, std::max(1, atoi(e)));
     if (const char* e = getenv("QCF_TARGET_CTAS")) ctx->target_ctas = std::max(1, atoi(e));
     if (ctx->rank < 0 || ctx->rank >= ctx->world) return fail(QCF_ERR_ARG, "rank outside [0, world_size)");
     if (ctx->block < 32 || ctx->block > 128 || ctx->block % 32) return fail(QCF_ERR_ARG, "block_threads must be 32, 64, 96 or 128");
@@ -598,7 +658,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     CK(upload(&ctx->d_fscale, ctx->fscale));
     CK(upload(&ctx->d_shoff, ctx->sh_off));
     CK(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < qcf_ctx::MAXSTREAM; ++s) {
         CK(cudaStreamCreateWithFlags(&ctx->streams[s], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ctx->ev_join[s], cudaEventDisableTiming));
     }
@@ -848,7 +908,7 @@ void qcf_destroy(qcf_ctx* ctx) {
     for (int k = 0; k < 2; ++k) { cudaFree(ctx->d_Pin[k]); cudaFree(ctx->d_Pk[k]); cudaFree(ctx->d_AK[k]); cudaFree(ctx->d_G[k]); }
     cudaFree(ctx->d_Pj); cudaFree(ctx->d_AJ); cudaFree(ctx->d_Dsh); cudaFree(ctx->d_dmax); cudaFree(ctx->d_counters);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-    for (int s = 0; s < 4; ++s) { if (ctx->streams[s]) cudaStreamDestroy(ctx->streams[s]); if (ctx->ev_join[s]) cudaEventDestroy(ctx->ev_join[s]); }
+    for (int s = 0; s < qcf_ctx::MAXSTREAM; ++s) { if (ctx->streams[s]) cudaStreamDestroy(ctx->streams[s]); if (ctx->ev_join[s]) cudaEventDestroy(ctx->ev_join[s]); }
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);

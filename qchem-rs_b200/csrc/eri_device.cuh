@@ -47,6 +47,7 @@ struct PairGroup {
     const int* fb;
     const int* sa;        // shell ids (density-block screening)
     const int* sb;
+    const int* nprim;     // primitive pairs kept for this pair (<= K; sorted by primitive Schwarz factor, negligible ones dropped)
     const double* Q;      // Schwarz factor
     const double* Qb;     // power-of-two bucket ceiling of Q, non-increasing along the list (prefix search)
     const double* prim;   // [K][PF_COUNT][npair];  PF_C = sqrt(2) pi^(5/4) c_a c_b exp(-mu AB^2) / p
@@ -371,12 +372,13 @@ __device__ __forceinline__ void contracted_quartet(const PairGroup& bra, int ib_
     if constexpr (LD > 0) {
         CDx = __ldg(ket.AB + ik_); CDy = __ldg(ket.AB + ket.npair + ik_); CDz = __ldg(ket.AB + 2 * (size_t)ket.npair + ik_);
     }
-    for (int kc = 0; kc < ket.K; ++kc) {
+    const int nkc = __ldg(ket.nprim + ik_), nkb = __ldg(bra.nprim + ib_);
+    for (int kc = 0; kc < nkc; ++kc) {
         double q, Qx, Qy, Qz, cQ;
         PairE<LC, LD> Ecd;
         load_prim<LC, LD>(ket, ik_, kc, CDx, CDy, CDz, q, Qx, Qy, Qz, cQ, Ecd, true);
         cQ *= scale;
-        for (int kb = 0; kb < bra.K; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
             double p, Px, Py, Pz, cP;
             PairE<LA, LB> Eab;
             load_prim<LA, LB>(bra, ib_, kb, ABx, ABy, ABz, p, Px, Py, Pz, cP, Eab, false);

@@ -76,115 +76,148 @@ __device__ __forceinline__ void ket_accumulate(const double (&R)[nherm(LA + LB +
             }
 }
 
-// bra transform + digestion of one slab group (compile-time SG) for one bra primitive
-template <int LA, int LB, int LC, int LD, int NK, int SPT, int SG>
-__device__ __forceinline__ void slab_digest(const double (&Hs)[SPT][nherm(LA + LB)], const double* __restrict__ e3,
-                                            const double* __restrict__ pab_s, double* __restrict__ jab_s,
-                                            double (&jab)[ncart(LA) * ncart(LB)], const BuildArgs& a, int fa, int fb, int fc, int fd) {
-    using C = SlabCfg<LA, LB, LC, LD, NK, SPT>;
-    using EL = E3Layout<LA, LB>;
-    constexpr int NA = C::NA, NB = C::NB, ND = C::ND;
-    const int N = a.N;
+// ---- bra transform + digestion of one slab group for one bra primitive -------------------------------
+// Every index is a template parameter (IA, IB, the slab group SG), so box sizes, E3 offsets and the
+// Hermite indices are constant expressions: Hsum stays in registers and no index arithmetic is executed.
+template <int NK, int SPT, int NB>
+struct DigestState {
     double pcd[SPT], scd[SPT];
     double pbd[NK][SPT][NB], pbc[NK][SPT][NB], kbc[NK][SPT][NB], kbd[NK][SPT][NB];
+    double pad[NK][SPT], pac[NK][SPT], kac[NK][SPT], kad[NK][SPT];
+};
+
+template <int LA, int LB, int SPT, int IAB>
+__device__ __forceinline__ void bra_value(const double (&Hs)[SPT][nherm(LA + LB)], const double* __restrict__ e3, double (&v)[SPT]) {
+    using EL = E3Layout<LA, LB>;
+    constexpr int nby = EL::bx(IAB, 1), nbz = EL::bx(IAB, 2), nbox = EL::box(IAB), off = EL::off(IAB);
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) v[s] = 0.0;
+#pragma unroll
+    for (int k2 = 0; k2 < nbox / 2; ++k2) {
+        const double2 ee = *reinterpret_cast<const double2*>(e3 + off + 2 * k2);
+        {
+            const int k = 2 * k2;
+            const int t = k / (nby * nbz), u = (k / nbz) % nby, w = k % nbz;
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) v[s] = fma(ee.x, Hs[s][hidx(t, u, w)], v[s]);
+        }
+        {
+            const int k = 2 * k2 + 1;
+            const int t = k / (nby * nbz), u = (k / nbz) % nby, w = k % nbz;
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) v[s] = fma(ee.y, Hs[s][hidx(t, u, w)], v[s]);
+        }
+    }
+    if constexpr (nbox & 1) {
+        constexpr int k = nbox - 1;
+        constexpr int t = k / (nby * nbz), u = (k / nbz) % nby, w = k % nbz;
+        const double e = e3[off + k];
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) v[s] = fma(e, Hs[s][hidx(t, u, w)], v[s]);
+    }
+}
+
+template <int LA, int LB, int LC, int LD, int NK, int SPT, int IA, int IB>
+__device__ __forceinline__ void digest_ab(const double (&Hs)[SPT][nherm(LA + LB)], const double* __restrict__ e3,
+                                          const double* __restrict__ pab_s, double* __restrict__ jab_s,
+                                          double (&jab)[ncart(LA) * ncart(LB)], DigestState<NK, SPT, ncart(LB)>& d) {
+    using C = SlabCfg<LA, LB, LC, LD, NK, SPT>;
+    constexpr int NB = C::NB, iab = IA * NB + IB;
+    double v[SPT];
+    bra_value<LA, LB, SPT, iab>(Hs, e3, v);
+    const double pab = pab_s[iab];
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) {
+        if constexpr (C::JSMEM) jab_s[iab * C::BLOCK] = fma(v[s], d.pcd[s], jab_s[iab * C::BLOCK]);
+        else jab[iab] = fma(v[s], d.pcd[s], jab[iab]);
+        d.scd[s] = fma(v[s], pab, d.scd[s]);
+#pragma unroll
+        for (int kk = 0; kk < NK; ++kk) {
+            d.kac[kk][s] = fma(v[s], d.pbd[kk][s][IB], d.kac[kk][s]);
+            d.kad[kk][s] = fma(v[s], d.pbc[kk][s][IB], d.kad[kk][s]);
+            d.kbc[kk][s][IB] = fma(v[s], d.pad[kk][s], d.kbc[kk][s][IB]);
+            d.kbd[kk][s][IB] = fma(v[s], d.pac[kk][s], d.kbd[kk][s][IB]);
+        }
+    }
+}
+
+template <int LA, int LB, int LC, int LD, int NK, int SPT, int IA, int... IB>
+__device__ __forceinline__ void digest_a(std::integer_sequence<int, IB...>, const int SG, const double (&Hs)[SPT][nherm(LA + LB)],
+                                         const double* __restrict__ e3, const double* __restrict__ pab_s,
+                                         double* __restrict__ jab_s, double (&jab)[ncart(LA) * ncart(LB)],
+                                         DigestState<NK, SPT, ncart(LB)>& d, const BuildArgs& a, int fa, int fc, int fd) {
+    constexpr int ND = ncart(LD);
+    const int N = a.N;
 #pragma unroll
     for (int s = 0; s < SPT; ++s) {
         const int icd = SG * SPT + s, IC = icd / ND, ID = icd % ND;
-        pcd[s] = __ldg(a.Pj + (size_t)(fc + IC) * N + fd + ID);
-        scd[s] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < NK; ++kk) {
+            const double* __restrict__ Pk = kk == 0 ? a.Pk0 : a.Pk1;
+            d.pad[kk][s] = __ldg(Pk + (size_t)(fa + IA) * N + fd + ID);
+            d.pac[kk][s] = __ldg(Pk + (size_t)(fa + IA) * N + fc + IC);
+            d.kac[kk][s] = 0.0; d.kad[kk][s] = 0.0;
+        }
+    }
+    (digest_ab<LA, LB, LC, LD, NK, SPT, IA, IB>(Hs, e3, pab_s, jab_s, jab, d), ...);
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) {
+        const int icd = SG * SPT + s, IC = icd / ND, ID = icd % ND;
+#pragma unroll
+        for (int kk = 0; kk < NK; ++kk) {
+            double* __restrict__ AK = kk == 0 ? a.AK0 : a.AK1;
+            red_add(AK + (size_t)(fa + IA) * N + fc + IC, d.kac[kk][s]);
+            red_add(AK + (size_t)(fa + IA) * N + fd + ID, d.kad[kk][s]);
+        }
+    }
+}
+
+template <int LA, int LB, int LC, int LD, int NK, int SPT, int... IA>
+__device__ __forceinline__ void digest_all_a(std::integer_sequence<int, IA...>, const int SG, const double (&Hs)[SPT][nherm(LA + LB)],
+                                             const double* __restrict__ e3, const double* __restrict__ pab_s,
+                                             double* __restrict__ jab_s, double (&jab)[ncart(LA) * ncart(LB)],
+                                             DigestState<NK, SPT, ncart(LB)>& d, const BuildArgs& a, int fa, int fc, int fd) {
+    (digest_a<LA, LB, LC, LD, NK, SPT, IA>(std::make_integer_sequence<int, ncart(LB)>{}, SG, Hs, e3, pab_s, jab_s, jab, d, a, fa, fc, fd), ...);
+}
+
+// The slab group enters only through the ket component offsets (IC, ID) of the global addresses, so it is a
+// runtime value here: one copy of the bra transform serves every slab group (code size, compile time).
+template <int LA, int LB, int LC, int LD, int NK, int SPT>
+__device__ __forceinline__ void slab_digest(const int SG, const double (&Hs)[SPT][nherm(LA + LB)], const double* __restrict__ e3,
+                                            const double* __restrict__ pab_s, double* __restrict__ jab_s,
+                                            double (&jab)[ncart(LA) * ncart(LB)], const BuildArgs& a, int fa, int fb, int fc, int fd) {
+    using C = SlabCfg<LA, LB, LC, LD, NK, SPT>;
+    constexpr int NA = C::NA, NB = C::NB, ND = C::ND;
+    const int N = a.N;
+    DigestState<NK, SPT, NB> d;
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) {
+        const int icd = SG * SPT + s, IC = icd / ND, ID = icd % ND;
+        d.pcd[s] = __ldg(a.Pj + (size_t)(fc + IC) * N + fd + ID);
+        d.scd[s] = 0.0;
 #pragma unroll
         for (int kk = 0; kk < NK; ++kk) {
             const double* __restrict__ Pk = kk == 0 ? a.Pk0 : a.Pk1;
 #pragma unroll
             for (int i = 0; i < NB; ++i) {
-                pbd[kk][s][i] = __ldg(Pk + (size_t)(fb + i) * N + fd + ID);
-                pbc[kk][s][i] = __ldg(Pk + (size_t)(fb + i) * N + fc + IC);
-                kbc[kk][s][i] = 0.0; kbd[kk][s][i] = 0.0;
+                d.pbd[kk][s][i] = __ldg(Pk + (size_t)(fb + i) * N + fd + ID);
+                d.pbc[kk][s][i] = __ldg(Pk + (size_t)(fb + i) * N + fc + IC);
+                d.kbc[kk][s][i] = 0.0; d.kbd[kk][s][i] = 0.0;
             }
         }
     }
-#pragma unroll
-    for (int ia = 0; ia < NA; ++ia) {
-        double pad[NK][SPT], pac[NK][SPT], kac[NK][SPT], kad[NK][SPT];
-#pragma unroll
-        for (int s = 0; s < SPT; ++s) {
-            const int icd = SG * SPT + s, IC = icd / ND, ID = icd % ND;
-#pragma unroll
-            for (int kk = 0; kk < NK; ++kk) {
-                const double* __restrict__ Pk = kk == 0 ? a.Pk0 : a.Pk1;
-                pad[kk][s] = __ldg(Pk + (size_t)(fa + ia) * N + fd + ID);
-                pac[kk][s] = __ldg(Pk + (size_t)(fa + ia) * N + fc + IC);
-                kac[kk][s] = 0.0; kad[kk][s] = 0.0;
-            }
-        }
-#pragma unroll
-        for (int ib = 0; ib < NB; ++ib) {
-            const int iab = ia * NB + ib;
-            const int nbx = EL::bx(iab, 0), nby = EL::bx(iab, 1), nbz = EL::bx(iab, 2);
-            const int nbox = nbx * nby * nbz;
-            const double* __restrict__ ep = e3 + EL::off(iab);
-            double v[SPT];
-#pragma unroll
-            for (int s = 0; s < SPT; ++s) v[s] = 0.0;
-#pragma unroll
-            for (int k2 = 0; k2 < (nbox + 1) / 2; ++k2) {
-                double e0, e1 = 0.0;
-                if (2 * k2 + 1 < nbox) {
-                    const double2 ee = *reinterpret_cast<const double2*>(ep + 2 * k2);
-                    e0 = ee.x; e1 = ee.y;
-                } else {
-                    e0 = ep[2 * k2];
-                }
-                {
-                    const int k = 2 * k2;
-                    const int t = k / (nby * nbz), u = (k / nbz) % nby, w = k % nbz;
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) v[s] = fma(e0, Hs[s][hidx(t, u, w)], v[s]);
-                }
-                if (2 * k2 + 1 < nbox) {
-                    const int k = 2 * k2 + 1;
-                    const int t = k / (nby * nbz), u = (k / nbz) % nby, w = k % nbz;
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) v[s] = fma(e1, Hs[s][hidx(t, u, w)], v[s]);
-                }
-            }
-            const double pab = pab_s[iab];
-#pragma unroll
-            for (int s = 0; s < SPT; ++s) {
-                if constexpr (C::JSMEM) jab_s[iab * C::BLOCK] = fma(v[s], pcd[s], jab_s[iab * C::BLOCK]);
-                else jab[iab] = fma(v[s], pcd[s], jab[iab]);
-                scd[s] = fma(v[s], pab, scd[s]);
-#pragma unroll
-                for (int kk = 0; kk < NK; ++kk) {
-                    kac[kk][s] = fma(v[s], pbd[kk][s][ib], kac[kk][s]);
-                    kad[kk][s] = fma(v[s], pbc[kk][s][ib], kad[kk][s]);
-                    kbc[kk][s][ib] = fma(v[s], pad[kk][s], kbc[kk][s][ib]);
-                    kbd[kk][s][ib] = fma(v[s], pac[kk][s], kbd[kk][s][ib]);
-                }
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < SPT; ++s) {
-            const int icd = SG * SPT + s, IC = icd / ND, ID = icd % ND;
-#pragma unroll
-            for (int kk = 0; kk < NK; ++kk) {
-                double* __restrict__ AK = kk == 0 ? a.AK0 : a.AK1;
-                red_add(AK + (size_t)(fa + ia) * N + fc + IC, kac[kk][s]);
-                red_add(AK + (size_t)(fa + ia) * N + fd + ID, kad[kk][s]);
-            }
-        }
-    }
+    digest_all_a<LA, LB, LC, LD, NK, SPT>(std::make_integer_sequence<int, NA>{}, SG, Hs, e3, pab_s, jab_s, jab, d, a, fa, fc, fd);
 #pragma unroll
     for (int s = 0; s < SPT; ++s) {
         const int icd = SG * SPT + s, IC = icd / ND, ID = icd % ND;
-        red_add(a.AJ + (size_t)(fc + IC) * N + fd + ID, scd[s]);
+        red_add(a.AJ + (size_t)(fc + IC) * N + fd + ID, d.scd[s]);
 #pragma unroll
         for (int kk = 0; kk < NK; ++kk) {
             double* __restrict__ AK = kk == 0 ? a.AK0 : a.AK1;
 #pragma unroll
             for (int i = 0; i < NB; ++i) {
-                red_add(AK + (size_t)(fb + i) * N + fc + IC, kbc[kk][s][i]);
-                red_add(AK + (size_t)(fb + i) * N + fd + ID, kbd[kk][s][i]);
+                red_add(AK + (size_t)(fb + i) * N + fc + IC, d.kbc[kk][s][i]);
+                red_add(AK + (size_t)(fb + i) * N + fd + ID, d.kbd[kk][s][i]);
             }
         }
     }
@@ -207,17 +240,6 @@ __device__ __forceinline__ void dispatch_ket(int sg, const double (&R)[nherm(LA 
         dispatch_ket<LA, LB, LC, LD, NK, SPT, SG + 1>(sg, R, Ecd, Hs);
     }
 }
-template <int LA, int LB, int LC, int LD, int NK, int SPT, int SG>
-__device__ __forceinline__ void dispatch_digest(int sg, const double (&Hs)[SPT][nherm(LA + LB)], const double* __restrict__ e3,
-                                                const double* __restrict__ pab_s, double* __restrict__ jab_s,
-                                                double (&jab)[ncart(LA) * ncart(LB)], const BuildArgs& a, int fa, int fb, int fc, int fd) {
-    if (sg == SG) {
-        slab_digest<LA, LB, LC, LD, NK, SPT, SG>(Hs, e3, pab_s, jab_s, jab, a, fa, fb, fc, fd);
-    } else if constexpr (SG + 1 < SlabCfg<LA, LB, LC, LD, NK, SPT>::G) {
-        dispatch_digest<LA, LB, LC, LD, NK, SPT, SG + 1>(sg, Hs, e3, pab_s, jab_s, jab, a, fa, fb, fc, fd);
-    }
-}
-
 template <int LA, int LB, int LC, int LD, int NK, int SPT>
 __global__ void __launch_bounds__(SlabCfg<LA, LB, LC, LD, NK, SPT>::BLOCK)
 eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
@@ -225,6 +247,7 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     using EL = E3Layout<LA, LB>;
     constexpr int NA = C::NA, NB = C::NB, NAB = C::NAB, L = C::L, NH = C::NH, G = C::G, NSUB = C::NSUB, BLOCK = C::BLOCK;
     extern __shared__ __align__(16) double smem[];
+    __shared__ int off_s[NAB];
     const int ib_ = a.rank + blockIdx.x * a.world;
     if (ib_ >= bra.npair) return;
     const double qab = __ldg(bra.Q + ib_);
@@ -240,7 +263,7 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     if (nket <= ket0) return;
     if (nket > ket0 + a.ket_chunk) nket = ket0 + a.ket_chunk;
 
-    const int N = a.N, KAB = bra.K;
+    const int N = a.N, KAB = __ldg(bra.nprim + ib_);
     const int fa = __ldg(bra.fa + ib_), fb = __ldg(bra.fb + ib_);
     const int sa = __ldg(bra.sa + ib_), sb = __ldg(bra.sb + ib_);
     const double bra_deg = (sa == sb) ? 0.5 : 1.0;
@@ -275,12 +298,14 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
             }
         }
         for (int i = threadIdx.x; i < NAB; i += BLOCK) pab_s[i] = __ldg(a.Pj + (size_t)(fa + i / NB) * N + fb + i % NB);
+#pragma unroll
+        for (int i = 0; i < NAB; ++i)
+            if (threadIdx.x == (i % BLOCK)) off_s[i] = EL::off(i);     // compile-time constants
         __syncthreads();
         for (int idx = threadIdx.x; idx < KAB * NAB; idx += BLOCK) {
             const int kb = idx / NAB, iab = idx % NAB;
             const int ia = iab / NB, ibb = iab % NB;
-            int off = 0;
-            for (int j = 0; j < iab; ++j) off += (EL::box(j) + 1) & ~1;
+            const int off = off_s[iab];
             double* tb = tab + (size_t)kb * EL::STRIDE;
             const double* ex = tb + EL::PRIM;
             const double* ey = ex + EL::EA_N;
@@ -329,6 +354,7 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
         if constexpr (LD > 0) {
             CDx = __ldg(ket.AB + ik_); CDy = __ldg(ket.AB + ket.npair + ik_); CDz = __ldg(ket.AB + 2 * (size_t)ket.npair + ik_);
         }
+        const int nkc = __ldg(ket.nprim + ik_);
         for (int kb = 0; kb < KAB; ++kb) {
             const double* __restrict__ tb = tab + (size_t)kb * EL::STRIDE;
             const double p = tb[0], Px = tb[1], Py = tb[2], Pz = tb[3], cP = tb[4] * deg;
@@ -337,7 +363,7 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
             for (int s = 0; s < SPT; ++s)
 #pragma unroll
                 for (int i = 0; i < NH; ++i) Hs[s][i] = 0.0;
-            for (int kc = 0; kc < ket.K; ++kc) {
+            for (int kc = 0; kc < nkc; ++kc) {
                 double q, Qx, Qy, Qz, cQ;
                 PairE<LC, LD> Ecd;
                 load_prim<LC, LD>(ket, ik_, kc, CDx, CDy, CDz, q, Qx, Qy, Qz, cQ, Ecd, true);
@@ -356,7 +382,7 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
                 hermite_R<L, false>(c, X, Y, Z, R);
                 dispatch_ket<LA, LB, LC, LD, NK, SPT, 0>(sg, R, Ecd, Hs);
             }
-            dispatch_digest<LA, LB, LC, LD, NK, SPT, 0>(sg, Hs, tb + EL::E3_OFF, pab_s, jab_s, jab, a, fa, fb, fc, fd);
+            slab_digest<LA, LB, LC, LD, NK, SPT>(sg, Hs, tb + EL::E3_OFF, pab_s, jab_s, jab, a, fa, fb, fc, fd);
         }
     }
 

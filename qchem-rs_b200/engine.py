@@ -39,7 +39,7 @@ class CStats(ctypes.Structure):
     _fields_ = [("n_basis", ctypes.c_int), ("n_shells", ctypes.c_int), ("n_pairs", ctypes.c_int),
                 ("n_groups", ctypes.c_int), ("quartets", ctypes.c_longlong), ("quartets_total", ctypes.c_longlong),
                 ("model_flops", ctypes.c_double), ("kernel_ms", ctypes.c_double), ("total_ms", ctypes.c_double),
-                ("launches", ctypes.c_int)]
+                ("launches", ctypes.c_int), ("prim_pairs", ctypes.c_longlong), ("prim_pairs_kept", ctypes.c_longlong)]
 
 
 class CLaunchRec(ctypes.Structure):
