@@ -79,7 +79,8 @@ struct Group {
 
 struct qcf_ctx {
     std::string err;
-    int device = 0, rank = 0, world = 1, block = 64, kets_per_thread = 8, target_ctas = 148 * 16;
+    int device = 0, rank = 0, world = 1, block = 64, kets_per_thread = 32, target_ctas = 296;
+    double serial_cap = 4e6;          // model flops one thread may run serially in one launch
     double tau = 1e-12;
     bool screening = true;
     // basis (host copies)
@@ -102,7 +103,7 @@ struct qcf_ctx {
     unsigned long long* d_counters = nullptr;
     int max_launch = 0;
     double* h_pin = nullptr;  // pinned staging, 2*N*N
-    static constexpr int MAXSTREAM = 16;
+    static constexpr int MAXSTREAM = 64;
     int nstreams = 8;
     cudaStream_t streams[MAXSTREAM] = {};
     cudaStream_t main_stream = nullptr;
@@ -478,37 +479,41 @@ int run_build(qcf_ctx* ctx, int mode, const double* dPa, const double* dPb, doub
     ctx->launches.clear();
     int nl = 0;
     const int ng = (int)ctx->groups.size();
-    // modelled-cost order, most expensive first, round-robin over the streams: the tail of the build is
-    // made of cheap kernels and every stream gets a similar share
-    struct Planned { int gi, gj; double cost; };
+    // Launch plan.  Kets per thread: long lists amortise the per-CTA prologue / J_ab reduction over many kets,
+    // short lists are cut finer so that the grid still fills the 148 SMs (d-bra classes, per-rank share of a
+    // multi-GPU run), and the serial work of one thread is capped so that highly contracted classes
+    // (K = 36 x 36 primitive quartets per shell quartet) do not become a latency tail.  Order: the launches
+    // whose threads run longest go first (they overlap with everything else), round-robin over the streams.
+    struct Planned { int gi, gj, nbra, nket_max, kpt; double serial, cost; };
     std::vector<Planned> plan;
     for (int gi = ng - 1; gi >= 0; --gi)
         for (int gj = gi; gj >= 0; --gj) {
             const Group& bra = ctx->groups[gi];
             const Group& ket = ctx->groups[gj];
             if (a.tau > 0.0 && q_bucket_ceiling(bra.pairs[0].Q) * q_bucket_ceiling(ket.pairs[0].Q) * a.dmax < a.tau) continue;
-            if ((bra.dev.npair - ctx->rank + ctx->world - 1) / ctx->world <= 0) continue;
-            const double nq = (double)bra.dev.npair * ket.dev.npair * (gi == gj ? 0.5 : 1.0);
-            plan.push_back({gi, gj, nq * ((double)bra.K * ket.K * model_flops_prim(bra.la, bra.lb, ket.la, ket.lb) + 400.0)});
-        }
-    std::stable_sort(plan.begin(), plan.end(), [](const Planned& x, const Planned& y) { return x.cost > y.cost; });
-    for (const Planned& pl : plan) {
-            const int gi = pl.gi, gj = pl.gj;
-            const Group& bra = ctx->groups[gi];
-            const Group& ket = ctx->groups[gj];
-            const ClassLaunch* cl = class_table(bra.cls, ket.cls);
             const int nbra = (bra.dev.npair - ctx->rank + ctx->world - 1) / ctx->world;
-            BuildArgs al = a;
-            al.counter = ctx->d_counters + nl;
+            if (nbra <= 0) continue;
             const int nket_max = gi == gj ? bra.dev.npair : ket.dev.npair;
-            // kets per thread: long lists amortise the per-CTA prologue / J_ab reduction over many kets, short
-            // lists are cut finer so that the grid still fills the 148 SMs (matters for the d-bra classes and
-            // for the per-rank share of a multi-GPU run)
+            const double per_quartet = (double)bra.K * ket.K * model_flops_prim(bra.la, bra.lb, ket.la, ket.lb) + 400.0;
             const bool slab = bra.la == 2 && bra.lb >= 1 && bra.la + bra.lb + ket.la + ket.lb <= 7;
             const int cta_threads = slab ? 128 : ctx->block;
             const long long want_chunks = (ctx->target_ctas + nbra - 1) / nbra;
             int kpt = (int)(nket_max / (want_chunks * cta_threads));
+            kpt = std::min(kpt, (int)(ctx->serial_cap / per_quartet));
             kpt = std::max(1, std::min(kpt, ctx->kets_per_thread));
+            const double nq = (double)bra.dev.npair * ket.dev.npair * (gi == gj ? 0.5 : 1.0);
+            plan.push_back({gi, gj, nbra, nket_max, kpt, kpt * per_quartet, nq * per_quartet});
+        }
+    std::stable_sort(plan.begin(), plan.end(), [](const Planned& x, const Planned& y) {
+        return x.serial != y.serial ? x.serial > y.serial : x.cost > y.cost;
+    });
+    for (const Planned& pl : plan) {
+            const int gi = pl.gi, gj = pl.gj, nbra = pl.nbra, nket_max = pl.nket_max, kpt = pl.kpt;
+            const Group& bra = ctx->groups[gi];
+            const Group& ket = ctx->groups[gj];
+            const ClassLaunch* cl = class_table(bra.cls, ket.cls);
+            BuildArgs al = a;
+            al.counter = ctx->d_counters + nl;
             if (ctx->profile) {
                 while ((int)ctx->prof_ev.size() < 2 * (nl + 1)) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
                 CK(cudaEventRecord(ctx->prof_ev[2 * nl], ctx->streams[0]));
@@ -611,6 +616,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     if (const char* e = getenv("QCF_PROFILE")) ctx->profile = (e[0] == '1');
     if (const char* e = getenv("QCF_KETS_PER_THREAD")) ctx->kets_per_thread = std::max(1, atoi(e));
     if (const char* e = getenv("QCF_STREAMS")) ctx->nstreams = std::min((int)qcf_ctx::MAXSTREAM, std::max(1, atoi(e)));
+    if (const char* e = getenv("QCF_SERIAL_CAP")) ctx->serial_cap = std::max(1.0, atof(e));
     if (const char* e = getenv("QCF_TARGET_CTAS")) ctx->target_ctas = std::max(1, atoi(e));
     if (ctx->rank < 0 || ctx->rank >= ctx->world) return fail(QCF_ERR_ARG, "rank outside [0, world_size)");
     if (ctx->block < 32 || ctx->block > 128 || ctx->block % 32) return fail(QCF_ERR_ARG, "block_threads must be 32, 64, 96 or 128");

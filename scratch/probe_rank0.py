@@ -1,0 +1,23 @@
+import sys, os
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import numpy as np
+from helpers import water_cluster
+from qchem_rs_b200 import hf, engine
+n = int(sys.argv[1]); world = int(sys.argv[2])
+system = water_cluster(n)
+P = np.load('/tmp/P.npy') if os.path.exists('/tmp/P.npy') else None
+if P is None:
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        ints = eng.one_electron()
+        seen = {}
+        class Tap:
+            def rhf(self, P):
+                seen['P'] = P.copy(); return eng.rhf(P)
+        hf.restricted_hartree_fock(system, hf.HartreeFockConfig(3, 1e-14), ints, Tap())
+        P = seen['P']; np.save('/tmp/P.npy', P)
+with engine.FockEngine(system, tau=1e-12, rank=0, world_size=world) as eng:
+    for _ in range(3): eng.rhf(P)
+    st = eng.stats(); print(os.environ.get("TAG",""), f"kernel_ms={st['kernel_ms']:.2f} total_ms={st['total_ms']:.2f} q={st['quartets']:.3e}")
+    if os.environ.get("QCF_PROFILE") == "1":
+        recs = eng.launch_profile(); print("sum launches ms", sum(r['ms'] for r in recs), "n", len(recs), "min", min(r['ms'] for r in recs))
+        small = sorted(r['ms'] for r in recs); print("median", small[len(small)//2], "count<0.02ms", sum(1 for x in small if x < 0.02))
