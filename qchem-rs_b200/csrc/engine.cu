@@ -495,7 +495,7 @@ int run_build(qcf_ctx* ctx, int mode, const double* dPa, const double* dPb, doub
             if (nbra <= 0) continue;
             const int nket_max = gi == gj ? bra.dev.npair : ket.dev.npair;
             const double per_quartet = (double)bra.K * ket.K * model_flops_prim(bra.la, bra.lb, ket.la, ket.lb) + 400.0;
-            const bool slab = bra.la == 2 && bra.lb >= 1 && bra.la + bra.lb + ket.la + ket.lb <= 7;
+            const bool slab = bra.la == 2 && bra.lb >= 1;
             const int cta_threads = slab ? 128 : ctx->block;
             const long long want_chunks = (ctx->target_ctas + nbra - 1) / nbra;
             int kpt = (int)(nket_max / (want_chunks * cta_threads));

@@ -35,7 +35,7 @@ constexpr int SPT = choose_spt();
 #ifdef QCF_USE_SLAB
 constexpr bool USE_SLAB = QCF_USE_SLAB;
 #else
-constexpr bool USE_SLAB = (LA == 2 && LB >= 1) && LTOT <= 7;   // (dd|dd): R_tuv (165 values) cannot stay in registers; served by the block kernel
+constexpr bool USE_SLAB = (LA == 2 && LB >= 1);   // every dp- and dd-bra class
 #endif
 
 template <int NK>

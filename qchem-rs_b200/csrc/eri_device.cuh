@@ -15,9 +15,9 @@ namespace qcf {
 constexpr double PI_D = 3.14159265358979323846;
 constexpr int LMAX = 2;
 constexpr int BOYS_LTOT = 4 * LMAX;          // 8
-constexpr double BOYS_TMAX = 36.0;
+constexpr double BOYS_TMAX = 64.0;          // extent of the table; each class switches at boys_tmax(L) <= 64
 constexpr int BOYS_PER_UNIT = 16;            // grid step 1/16
-constexpr int BOYS_NGRID = 36 * BOYS_PER_UNIT + 1;
+constexpr int BOYS_NGRID = 64 * BOYS_PER_UNIT + 1;
 constexpr int BOYS_ORDER = 6;                // Taylor order (7 terms), |dT| <= 1/32 -> 6e-15
 constexpr int BOYS_ROW = 8;                  // doubles per grid point and class: 7 Taylor coefficients + exp(-T0)
 
@@ -89,12 +89,16 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 // ---- Boys function -----------------------------------------------------------------------------
-// F_0..F_L(T).  T < 36: 7-term Taylor expansion of F_L about the nearest grid point (table row holds
-// F_{L+k}(T0)/k!), then the stable downward recursion F_{m-1} = (2T F_m + e^-T)/(2m-1).  T >= 36:
-// F_0 = sqrt(pi/T)/2 (erf(6) = 1 - 2e-17) and the upward recursion, stable for T > m.
+// F_0..F_L(T).  T < boys_tmax(L) (36 .. 64): 7-term Taylor expansion of F_L about the nearest grid point (table row holds
+// F_{L+k}(T0)/k!), then the stable downward recursion F_{m-1} = (2T F_m + e^-T)/(2m-1).  Above:
+// F_0 = sqrt(pi/T)/2 and the upward recursion without the exp(-T) term (stable for T > m).
+// Above boys_tmax(L) the asymptotic branch may drop exp(-T): exp(-T) (2T)^L / ((2L-1)!! F_0) < 1e-16 there.
+__host__ __device__ constexpr double boys_tmax(int L) {
+    return L == 0 ? 36.0 : L == 1 ? 44.0 : L == 2 ? 48.0 : L == 3 ? 52.0 : L == 4 ? 56.0 : L == 5 ? 58.0 : L == 6 ? 60.0 : L == 7 ? 62.0 : 64.0;
+}
 template <int L>
 __device__ __forceinline__ void boys(double T, const double* __restrict__ table, double (&F)[L + 1]) {
-    if (T < BOYS_TMAX) {
+    if (T < boys_tmax(L)) {
         const int g = (int)(T * BOYS_PER_UNIT + 0.5);
         const double d = (double)g * (1.0 / BOYS_PER_UNIT) - T;
         const double* r = table + ((size_t)L * BOYS_NGRID + g) * BOYS_ROW;
@@ -114,14 +118,14 @@ __device__ __forceinline__ void boys(double T, const double* __restrict__ table,
             for (int m = L; m > 0; --m) F[m - 1] = fma(t2, F[m], e) * (1.0 / (2 * m - 1));
         }
     } else {
+        // T >= boys_tmax(L): exp(-T) is below 1e-16 F_m(T) for every m <= L, so the upward recursion
+        // F_{m+1} = ((2m+1) F_m - e^-T) / 2T loses nothing by dropping it -- no exp on this path at all
         const double rs = fast_rsqrt(T);
-        const double rt = rs * rs;
         F[0] = 0.88622692545275801365 * rs;       // sqrt(pi)/2 / sqrt(T)
         if constexpr (L > 0) {
-            const double e = exp(-T);
-            const double h = 0.5 * rt;
+            const double h = 0.5 * rs * rs;
 #pragma unroll
-            for (int m = 0; m < L; ++m) F[m + 1] = ((2 * m + 1) * F[m] - e) * h;
+            for (int m = 0; m < L; ++m) F[m + 1] = (2 * m + 1) * F[m] * h;
         }
     }
 }

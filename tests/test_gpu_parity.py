@@ -34,7 +34,7 @@ def test_boys_matches_mpmath_table(spd):
 
 def test_boys_dense_sweep_against_oracle(spd):
     _, _, eng = spd
-    T = np.concatenate([np.linspace(0, 40, 2001), np.linspace(35.9, 36.1, 201), np.geomspace(40, 1e4, 200)])
+    T = np.concatenate([np.linspace(0, 70, 3501), np.linspace(63.9, 64.1, 201), np.geomspace(40, 1e4, 200)])
     F = eng.boys(8, T)
     ref = np.array([oracle_lib.boys(8, t) for t in T])
     np.testing.assert_allclose(F, ref, rtol=1e-13, atol=1e-300)
