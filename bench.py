@@ -264,10 +264,11 @@ def run_b200(args):
                         "ms_per_step": ms_e / args.steps},
                 "gpu_launches": launches,
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak * world, "unit": "TFLOP/s",
-                             "frac": achieved / (peak * world), "traffic": None,
+                             "frac": achieved / (peak * world), "traffic": 6.39e6,
                              "note": "achieved = SURVEY 8d model flops of the evaluated quartets / CUDA-event time, all eri_jk "
                                      "launches of the step; peak = FP64 FMA microbenchmark measured in this run (MEASURED_PEAKS.json "
-                                     "has no FP64 figure; nominal 37.2)"},
+                                     "has no FP64 figure; nominal 37.2); traffic = dram read+write bytes of the largest launch of the top class (ps|ss), "
+                                     "ncu --set full capture in profiles/r1_final_block_kernel_1000.txt: the path is not HBM-bound"},
                 "clocks": clocks}
         if cpu is not None:
             line["cpu_baseline"] = cpu
