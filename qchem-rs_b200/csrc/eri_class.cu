@@ -64,8 +64,16 @@ void launch_jk(int nk, int nbra, int nket_max, int block, int kpt, cudaStream_t 
     } else {
         a.ket_chunk = block * kpt;
         const dim3 grid(nbra, (nket_max + a.ket_chunk - 1) / a.ket_chunk);
-        if (nk == 1) eri_jk_kernel<LA, LB, LC, LD, 1><<<grid, block, 0, s>>>(bra, ket, a, same);
-        else eri_jk_kernel<LA, LB, LC, LD, 2><<<grid, block, 0, s>>>(bra, ket, a, same);
+        // dynamic shared memory: staged bra primitives + two rows of the shell-block density maxima
+        const size_t smem = (size_t)bra.K * BRA_S * sizeof(double) + 2 * (size_t)a.nshell * sizeof(float);
+        static size_t smem_set = 48 * 1024;
+        if (smem > smem_set) {
+            cudaFuncSetAttribute(eri_jk_kernel<LA, LB, LC, LD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(eri_jk_kernel<LA, LB, LC, LD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            smem_set = smem;
+        }
+        if (nk == 1) eri_jk_kernel<LA, LB, LC, LD, 1><<<grid, block, smem, s>>>(bra, ket, a, same);
+        else eri_jk_kernel<LA, LB, LC, LD, 2><<<grid, block, smem, s>>>(bra, ket, a, same);
     }
 }
 void launch_quartet(cudaStream_t s, const PairGroup& bra, int ib_, const PairGroup& ket, int ik_, const double* boys, double* out) {

@@ -391,6 +391,59 @@ __device__ __forceinline__ void contracted_quartet(const PairGroup& bra, int ib_
     }
 }
 
+// ---- bra primitives staged in shared memory (block kernel) ------------------------------------------
+// The bra pair is fixed per CTA: its primitive data (p, P, prefactor, P-A and 1/2p) is copied once into shared
+// memory and read back as broadcast LDS -- no global address arithmetic and no reciprocal per primitive quartet.
+constexpr int BRA_S = 9;    // doubles per staged bra primitive: PrimField order, then 1/(2p)
+__device__ __forceinline__ void stage_bra(const PairGroup& g, int ib_, int nkb, double* __restrict__ dst) {
+    for (int t = threadIdx.x; t < nkb * BRA_S; t += blockDim.x) {
+        const int kb = t / BRA_S, f = t % BRA_S;
+        const double* base = g.prim + (size_t)kb * PF_COUNT * g.npair + ib_;
+        dst[t] = f < PF_COUNT ? __ldg(base + (size_t)f * g.npair) : 0.5 / __ldg(base + (size_t)PF_P * g.npair);
+    }
+}
+template <int LA, int LB>
+__device__ __forceinline__ void load_prim_staged(const double* __restrict__ b, double ABx, double ABy, double ABz,
+                                                 double& p, double& Px, double& Py, double& Pz, double& cP, PairE<LA, LB>& E) {
+    p = b[PF_P]; Px = b[PF_PX]; Py = b[PF_PY]; Pz = b[PF_PZ]; cP = b[PF_C];
+    if constexpr (LA + LB > 0) {
+        const double h = b[PF_COUNT];
+        const double pax = b[PF_PAX], pay = b[PF_PAY], paz = b[PF_PAZ];
+        E.ax[0].build(h, pax, pax + ABx, false);
+        E.ax[1].build(h, pay, pay + ABy, false);
+        E.ax[2].build(h, paz, paz + ABz, false);
+    } else {
+        E.ax[0].e[0] = 1.0; E.ax[1].e[0] = 1.0; E.ax[2].e[0] = 1.0;
+    }
+}
+// contracted quartet block with the bra primitives read from the staged copy
+template <int LA, int LB, int LC, int LD>
+__device__ __forceinline__ void contracted_quartet_staged(const double* __restrict__ bra_s, int nkb, double ABx, double ABy, double ABz,
+                                                          const PairGroup& ket, int ik_, double scale,
+                                                          const double* __restrict__ boys_table,
+                                                          double (&I)[ncart(LA) * ncart(LB) * ncart(LC) * ncart(LD)]) {
+    constexpr int NI = ncart(LA) * ncart(LB) * ncart(LC) * ncart(LD);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) I[i] = 0.0;
+    double CDx = 0, CDy = 0, CDz = 0;
+    if constexpr (LD > 0) {
+        CDx = __ldg(ket.AB + ik_); CDy = __ldg(ket.AB + ket.npair + ik_); CDz = __ldg(ket.AB + 2 * (size_t)ket.npair + ik_);
+    }
+    const int nkc = __ldg(ket.nprim + ik_);
+    for (int kc = 0; kc < nkc; ++kc) {
+        double q, Qx, Qy, Qz, cQ;
+        PairE<LC, LD> Ecd;
+        load_prim<LC, LD>(ket, ik_, kc, CDx, CDy, CDz, q, Qx, Qy, Qz, cQ, Ecd, true);
+        cQ *= scale;
+        for (int kb = 0; kb < nkb; ++kb) {
+            double p, Px, Py, Pz, cP;
+            PairE<LA, LB> Eab;
+            load_prim_staged<LA, LB>(bra_s + kb * BRA_S, ABx, ABy, ABz, p, Px, Py, Pz, cP, Eab);
+            prim_quartet<LA, LB, LC, LD>(Eab, Ecd, p, q, Px - Qx, Py - Qy, Pz - Qz, cP * cQ, boys_table, I);
+        }
+    }
+}
+
 __device__ __forceinline__ void red_add(double* addr, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
@@ -524,6 +577,25 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     const double bra_deg = (sa == sb) ? 0.5 : 1.0;
     const float dab = __ldg(a.Dsh + (size_t)sa * a.nshell + sb);
 
+    // CTA-constant data in shared memory: the bra primitives and the two rows (shell a, shell b) of the
+    // shell-block density maxima that the exchange screening gathers from
+    extern __shared__ __align__(16) double dyn_s[];
+    const int nkb = __ldg(bra.nprim + ib_);
+    double* const bra_s = dyn_s;                                                     // [bra.K][BRA_S]
+    float* const dsh_a = reinterpret_cast<float*>(dyn_s + (size_t)bra.K * BRA_S);    // [nshell]
+    float* const dsh_b = dsh_a + a.nshell;                                           // [nshell]
+    stage_bra(bra, ib_, nkb, bra_s);
+    if (a.tau > 0.0)
+        for (int t = threadIdx.x; t < a.nshell; t += blockDim.x) {
+            dsh_a[t] = __ldg(a.Dsh + (size_t)sa * a.nshell + t);
+            dsh_b[t] = __ldg(a.Dsh + (size_t)sb * a.nshell + t);
+        }
+    double ABx = 0, ABy = 0, ABz = 0;
+    if constexpr (LB > 0) {
+        ABx = __ldg(bra.AB + ib_); ABy = __ldg(bra.AB + bra.npair + ib_); ABz = __ldg(bra.AB + 2 * (size_t)bra.npair + ib_);
+    }
+    __syncthreads();
+
     double jab[NAB];
     double pab[NAB];
 #pragma unroll
@@ -535,8 +607,7 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
         const int sc = __ldg(ket.sa + ik_), sd = __ldg(ket.sb + ik_);
         if (a.tau > 0.0) {
             float dm = fmaxf(dab, __ldg(a.Dsh + (size_t)sc * a.nshell + sd));
-            float dk = fmaxf(fmaxf(__ldg(a.Dsh + (size_t)sa * a.nshell + sc), __ldg(a.Dsh + (size_t)sa * a.nshell + sd)),
-                             fmaxf(__ldg(a.Dsh + (size_t)sb * a.nshell + sc), __ldg(a.Dsh + (size_t)sb * a.nshell + sd)));
+            float dk = fmaxf(fmaxf(dsh_a[sc], dsh_a[sd]), fmaxf(dsh_b[sc], dsh_b[sd]));
             dm = fmaxf(dm, 0.5f * dk);
             if (qab * qcd * (double)dm < a.tau) continue;
         }
@@ -546,7 +617,7 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
         if (same_group && ik_ == ib_) deg *= 0.5;
 
         double I[NI];
-        contracted_quartet<LA, LB, LC, LD>(bra, ib_, ket, ik_, deg, a.boys, I);
+        contracted_quartet_staged<LA, LB, LC, LD>(bra_s, nkb, ABx, ABy, ABz, ket, ik_, deg, a.boys, I);
 
         double kacc[NK * KA::SIZE];
 #pragma unroll
