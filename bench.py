@@ -10,7 +10,7 @@ iteration `--scf-iters` of that system (not random: density-weighted screening i
   python bench.py --impl reference ...                     the reference algorithm on the host cores
 
 `value`  : unique shell quartets evaluated per second, whole job, P resident in HBM.
-`e2e`    : same metric through the host API (pinned host P -> H2D -> build -> allreduce -> D2H G).
+`e2e`    : same metric through the host API (P in pinned host memory -> H2D -> build -> allreduce -> D2H G, pinned).
 `roofline`: SURVEY.md 8d model flops of the evaluated quartets / CUDA-event time / measured FP64 FMA peak.
 The oracle is used ONLY in the cpu_baseline / --impl reference legs (it is the CPU restatement of the
 reference; the reference itself needs cargo + the absent `molint` crate and cannot be built).
@@ -246,7 +246,13 @@ def run_b200(args):
     with ClockSampler(local) as clk:
         ms, q, fl, launches = timed(lambda: fock.rhf_device(), args.steps, args.warmup)
     clocks = clk.summary()
-    ms_e, q_e, _, _ = timed(lambda: fock.rhf(P), args.steps, max(1, args.warmup // 2))
+    # e2e: the density lives in pinned host memory (the engine's staging buffer); every step copies it to the
+    # device, builds, all-reduces and reads the Fock matrix back into pinned host memory
+    # (N = 1: the drop-in C-ABI call itself, qcf_build_rhf with caller-owned host buffers; N > 1: pinned buffers +
+    # NCCL all-reduce, since the C ABI leaves the reduction to the caller)
+    fock.hP[0].copy_(torch.from_numpy(P))
+    e2e_call = (lambda: eng.rhf(P)) if world == 1 else (lambda: fock.rhf_pinned())
+    ms_e, q_e, _, _ = timed(e2e_call, args.steps, max(1, args.warmup // 2))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -103,6 +103,16 @@ class DeviceFock:
         torch.cuda.current_stream(self.dev).synchronize()
         return self.hG[0].numpy().copy()
 
+    def rhf_pinned(self) -> torch.Tensor:
+        """Same as `rhf`, for callers that keep the density in the engine's pinned staging buffer `hP[0]`
+        (a `DMatrix` allocated there on the Rust side): H2D from pinned memory, build, all-reduce, D2H into
+        the pinned `hG[0]`, which is returned as a view (valid until the next call)."""
+        self.dP[0].copy_(self.hP[0], non_blocking=True)
+        self.rhf_device()
+        self.hG[0].copy_(self.dG[0], non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self.hG[0]
+
     def uhf(self, Pa: np.ndarray, Pb: np.ndarray):
         self.hP[0].copy_(torch.from_numpy(np.ascontiguousarray(Pa, dtype=np.float64)))
         self.hP[1].copy_(torch.from_numpy(np.ascontiguousarray(Pb, dtype=np.float64)))
