@@ -1,17 +1,27 @@
-import sys, time, os
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import time
+import sys, os
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
 import numpy as np
-from helpers import water_cluster, oracle_lib, load_system
-from qchem_rs_b200 import hf, engine
+import qcpkg
+pkg = qcpkg.load()
+from qchem_rs_b200 import hf, engine, molecules
+from qchem_rs_b200.basis import BasisSet, MolecularSystem
+
+
+def water_cluster(n, basis="6-31G_st"):
+    bs = BasisSet.load(ROOT / "data" / "basis" / f"{basis}.json")
+    return MolecularSystem.from_atoms(molecules.water_cluster(n), bs)
 
 ns = [int(x) for x in sys.argv[1].split(',')]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 for n in ns:
     system = water_cluster(n)
     fb = system.flat()
-    t0 = time.time(); ints = oracle_lib.one_electron(fb); t1 = time.time()
-    print(f"n={n} N={fb.n_basis} 1e ints {t1-t0:.2f}s", flush=True)
+    print(f"n={n} N={fb.n_basis}", flush=True)
     with engine.FockEngine(system, tau=1e-12) as eng:
+        ints = eng.one_electron()
         if n == ns[0]:
             print("fp64 peak TF", eng.fp64_peak_tflops())
         class B:

@@ -1,8 +1,18 @@
 import sys, os
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
 import numpy as np
-from helpers import water_cluster
-from qchem_rs_b200 import hf, engine
+import qcpkg
+pkg = qcpkg.load()
+from qchem_rs_b200 import hf, engine, molecules
+from qchem_rs_b200.basis import BasisSet, MolecularSystem
+
+
+def water_cluster(n, basis="6-31G_st"):
+    bs = BasisSet.load(ROOT / "data" / "basis" / f"{basis}.json")
+    return MolecularSystem.from_atoms(molecules.water_cluster(n), bs)
+
 n = int(sys.argv[1]); world = int(sys.argv[2])
 system = water_cluster(n)
 P = np.load('/tmp/P.npy') if os.path.exists('/tmp/P.npy') else None
