@@ -99,6 +99,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def hbm_note():
+    """DRAM side of the roofline for the largest launch of the top class, (ps|ss) K = 3x3, from the committed
+    ncu --set full capture (profiles/r1_final_block_kernel_1000.txt): 6.39 MB read+written in 0.588 ms."""
+    peak = 6524.3
+    try:
+        peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+    except Exception:
+        pass
+    achieved = 6.39e6 / 0.588e-3 / 1e9
+    return {"achieved_gbs": achieved, "peak_gbs": peak, "frac": achieved / peak,
+            "source": "ncu capture in profiles/ (not measured live); the path is FP64-pipe bound, not HBM bound"}
+
+
 def scf_density(pkg, system, ints, builder, iters):
     """Density that enters the Fock build of SCF iteration `iters` (0 = the Hueckel guess), produced by
     the reference's own RHF loop (qchem-rs_b200/hf.py restates rhf.rs:32-108) driving `builder`."""
@@ -271,6 +284,7 @@ def run_b200(args):
                 "gpu_launches": launches,
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak * world, "unit": "TFLOP/s",
                              "frac": achieved / (peak * world), "traffic": 6.39e6,
+                             "hbm": hbm_note(),
                              "note": "achieved = SURVEY 8d model flops of the evaluated quartets / CUDA-event time, all eri_jk "
                                      "launches of the step; peak = FP64 FMA microbenchmark measured in this run (MEASURED_PEAKS.json "
                                      "has no FP64 figure; nominal 37.2); traffic = dram read+write bytes of the largest launch of the top class (ps|ss), "
