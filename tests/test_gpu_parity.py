@@ -356,3 +356,26 @@ def test_water_cluster_5_scf_against_direct_oracle():
     assert got.iterations == ref.iterations
     assert abs(got.total_energy() - ref.total_energy()) < E_TOL
     assert np.max(np.abs(got.fock - ref.fock)) < F_TOL
+
+
+def test_device_resident_paths_match_host_calls():
+    """qcf_build_rhf_dev / qcf_build_uhf_dev on torch's current stream (the multi-GPU product path,
+    qchem-rs_b200/distributed.py::DeviceFock, world size 1 here) against the host-buffer C-ABI calls."""
+    import torch
+    from qchem_rs_b200 import distributed
+    system = water_cluster(2)
+    n = system.n_basis()
+    P, Pb = random_symmetric_density(n, 5), random_symmetric_density(n, 6)
+    dev = torch.device("cuda", 0)
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        fock = distributed.DeviceFock(eng, dev)
+        g_host = eng.rhf(P)
+        np.testing.assert_allclose(fock.rhf(P), g_host, atol=1e-12)
+        fock.hP[0].copy_(torch.from_numpy(P))
+        np.testing.assert_allclose(fock.rhf_pinned().numpy(), g_host, atol=1e-12)
+        ga, gb = eng.uhf(P, Pb)
+        da, db = fock.uhf(P, Pb)
+        np.testing.assert_allclose(da, ga, atol=1e-12)
+        np.testing.assert_allclose(db, gb, atol=1e-12)
+        prof = eng.launch_profile()
+        assert len(prof) > 0 and sum(r["quartets"] for r in prof) == eng.stats()["quartets"]
