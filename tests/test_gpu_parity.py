@@ -379,3 +379,49 @@ def test_device_resident_paths_match_host_calls():
         np.testing.assert_allclose(db, gb, atol=1e-12)
         prof = eng.launch_profile()
         assert len(prof) > 0 and sum(r["quartets"] for r in prof) == eng.stats()["quartets"]
+
+
+def test_gpu_quartets_permutational_symmetry_and_schwarz_bound(spd):
+    """Invariants of the device integrals themselves: 8-fold permutational symmetry and
+    |(ab|cd)| <= sqrt(max (ab|ab)) sqrt(max (cd|cd)) for random shell quartets of the s/p/d test system."""
+    _, _, eng = spd
+    rng = np.random.default_rng(17)
+    ns = 12
+    qmax = {}
+
+    def q(a, b):
+        if (a, b) not in qmax:
+            blk = eng.eri_quartet(a, b, a, b)
+            qmax[(a, b)] = float(np.sqrt(np.max(np.abs(np.einsum("ijij->ij", blk)))))
+        return qmax[(a, b)]
+    for _ in range(40):
+        a, b, c, d = (int(x) for x in rng.integers(0, ns, size=4))
+        v = eng.eri_quartet(a, b, c, d)
+        np.testing.assert_allclose(eng.eri_quartet(b, a, c, d), v.transpose(1, 0, 2, 3), atol=1e-13)
+        np.testing.assert_allclose(eng.eri_quartet(a, b, d, c), v.transpose(0, 1, 3, 2), atol=1e-13)
+        np.testing.assert_allclose(eng.eri_quartet(c, d, a, b), v.transpose(2, 3, 0, 1), atol=1e-13)
+        assert np.max(np.abs(v)) <= q(a, b) * q(c, d) * (1 + 1e-10) + 1e-14
+
+
+def test_scf_energy_is_rotation_and_translation_invariant_on_gpu():
+    """(H2O)_2 / 6-31G* (Cartesian d shells): E_total from the engine-driven SCF is invariant under a rigid
+    rotation + translation of the molecule.  The reference's Hueckel guess is not rotation-covariant (rhf.rs:139-143
+    scales the diagonal too), so the two runs follow different trajectories and stop at slightly different points of
+    a first-order energy expression: 5e-8 Eh is asserted (observed 1.4e-9)."""
+    from qchem_rs_b200.basis import MolecularSystem, Atom, BasisSet
+    from helpers import DATA
+    bs = BasisSet.load(DATA / "basis" / "6-31G_st.json")
+    atoms = water_cluster(2).atoms
+    th, ph = 0.7, -1.1
+    rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    rx = np.array([[1, 0, 0], [0, np.cos(ph), -np.sin(ph)], [0, np.sin(ph), np.cos(ph)]])
+    rot = rz @ rx
+    moved = [Atom(a.ordinal, rot @ a.position + np.array([1.5, -2.0, 0.75])) for a in atoms]
+    energies = []
+    for at in (atoms, moved):
+        system = MolecularSystem.from_atoms(at, bs)
+        with engine.FockEngine(system, tau=1e-12) as eng:
+            out = hf.restricted_hartree_fock(system, hf.HartreeFockConfig(100, 1e-9), eng.one_electron(), eng)
+        assert out is not None
+        energies.append(out.total_energy())
+    assert abs(energies[0] - energies[1]) < 5e-8
