@@ -107,7 +107,7 @@ struct qcf_ctx {
     int nstreams = 8;
     cudaStream_t streams[MAXSTREAM] = {};
     cudaStream_t main_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join[MAXSTREAM] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join[MAXSTREAM] = {}, ev_t0 = nullptr, ev_t1 = nullptr, ev_h0 = nullptr, ev_h1 = nullptr;
     // stats of the last build
     struct LaunchRec { int bra, ket; float ms = 0; };
     bool profile = false;                 // QCF_PROFILE=1: serialise the class launches and time each one
@@ -566,8 +566,7 @@ int collect_stats(qcf_ctx* ctx) {
 int host_build(qcf_ctx* ctx, int mode, const double* Pa, const double* Pb, double* G0, double* G1) {
     const size_t nn = (size_t)ctx->N * ctx->N;
     cudaStream_t ms = ctx->main_stream;
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    cudaEvent_t e0 = ctx->ev_h0, e1 = ctx->ev_h1;
     CK(cudaEventRecord(e0, ms));
     std::memcpy(ctx->h_pin, Pa, nn * sizeof(double));
     CK(cudaMemcpyAsync(ctx->d_Pin[0], ctx->h_pin, nn * sizeof(double), cudaMemcpyHostToDevice, ms));
@@ -586,7 +585,6 @@ int host_build(qcf_ctx* ctx, int mode, const double* Pa, const double* Pb, doubl
     float t = 0;
     CK(cudaEventElapsedTime(&t, e0, e1));
     ctx->stats.total_ms = t;
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return collect_stats(ctx);
 }
 
@@ -673,6 +671,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     }
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreate(&ctx->ev_t0)); CK(cudaEventCreate(&ctx->ev_t1));
+    CK(cudaEventCreate(&ctx->ev_h0)); CK(cudaEventCreate(&ctx->ev_h1));
     int rc = build_pairs(ctx);
     if (rc) return rc;
     for (int k = 0; k < 2; ++k) {
@@ -922,6 +921,9 @@ void qcf_destroy(qcf_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->ev_h0) cudaEventDestroy(ctx->ev_h0);
+    if (ctx->ev_h1) cudaEventDestroy(ctx->ev_h1);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     delete ctx;
 }
 

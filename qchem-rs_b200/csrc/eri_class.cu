@@ -44,11 +44,9 @@ void launch_slab(int nbra, int nket_max, int kpt, cudaStream_t s, const PairGrou
         using C = SlabCfg<LA, LB, LC, LD, NK, SPT>;
         auto kern = eri_jk_slab_kernel<LA, LB, LC, LD, NK, SPT>;
         const size_t smem = slab_smem_bytes<LA, LB, LC, LD, NK, SPT>(bra.K);
-        static size_t smem_set = 0;
-        if (smem > smem_set) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            smem_set = smem;
-        }
+        // opt in to more than 48 KB of dynamic shared memory (per device and per function, so it is not cached in
+        // a process-wide flag: one process may hold contexts on several devices)
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         a.ket_chunk = 32 * C::NSUB * kpt;
         const dim3 grid(nbra, (nket_max + a.ket_chunk - 1) / a.ket_chunk, C::G);
         kern<<<grid, C::BLOCK, smem, s>>>(bra, ket, a, same);
@@ -66,11 +64,9 @@ void launch_jk(int nk, int nbra, int nket_max, int block, int kpt, cudaStream_t 
         const dim3 grid(nbra, (nket_max + a.ket_chunk - 1) / a.ket_chunk);
         // dynamic shared memory: staged bra primitives + two rows of the shell-block density maxima
         const size_t smem = (size_t)bra.K * BRA_S * sizeof(double) + 2 * (size_t)a.nshell * sizeof(float);
-        static size_t smem_set = 48 * 1024;
-        if (smem > smem_set) {
-            cudaFuncSetAttribute(eri_jk_kernel<LA, LB, LC, LD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(eri_jk_kernel<LA, LB, LC, LD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            smem_set = smem;
+        if (smem > 48 * 1024) {
+            if (nk == 1) cudaFuncSetAttribute(eri_jk_kernel<LA, LB, LC, LD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            else cudaFuncSetAttribute(eri_jk_kernel<LA, LB, LC, LD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
         if (nk == 1) eri_jk_kernel<LA, LB, LC, LD, 1><<<grid, block, smem, s>>>(bra, ket, a, same);
         else eri_jk_kernel<LA, LB, LC, LD, 2><<<grid, block, smem, s>>>(bra, ket, a, same);

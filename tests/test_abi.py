@@ -50,3 +50,28 @@ def test_create_fails_loudly_without_cuda_device():
     from qchem_rs_b200 import engine
     with pytest.raises(engine.FockError, match="CUDA|cuda"):
         engine.FockEngine(load_system("water", "STO-3G"))
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct in include/qcfock.h, as compiled by gcc, against the ctypes mirrors
+    the Python binding (and the Rust #[repr(C)] structs of INTEGRATION.md) are written from."""
+    import ctypes
+    import subprocess
+    from qchem_rs_b200 import engine
+    from qchem_rs_b200.basis import CBasis
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "qcfock.h"\n'
+        'int main(void) {\n'
+        '  printf("%zu %zu %zu %zu\\n", sizeof(qcf_basis), sizeof(qcf_opts), sizeof(qcf_stats_t), sizeof(qcf_launch_rec));\n'
+        '  printf("%zu %zu %zu %zu\\n", offsetof(qcf_basis, cartesian), offsetof(qcf_opts, block_threads),\n'
+        '         offsetof(qcf_stats_t, prim_pairs_kept), offsetof(qcf_launch_rec, ms));\n'
+        '  return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    sizes = [int(x) for x in out[:4]]
+    offs = [int(x) for x in out[4:]]
+    assert sizes == [ctypes.sizeof(CBasis), ctypes.sizeof(engine.COpts), ctypes.sizeof(engine.CStats), ctypes.sizeof(engine.CLaunchRec)]
+    assert offs == [CBasis.cartesian.offset, engine.COpts.block_threads.offset, engine.CStats.prim_pairs_kept.offset,
+                    engine.CLaunchRec.ms.offset]
