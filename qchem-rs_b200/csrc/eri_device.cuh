@@ -602,15 +602,37 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     for (int i = 0; i < NAB; ++i) { jab[i] = 0.0; pab[i] = __ldg(a.Pj + (size_t)(fa + i / NB) * N + fb + i % NB); }
     unsigned int nq = 0;
 
-    for (int ik_ = ket0 + threadIdx.x; ik_ < nket; ik_ += blockDim.x) {
-        const double qcd = __ldg(ket.Q + ik_);
-        const int sc = __ldg(ket.sa + ik_), sd = __ldg(ket.sb + ik_);
-        if (a.tau > 0.0) {
-            float dm = fmaxf(dab, __ldg(a.Dsh + (size_t)sc * a.nshell + sd));
-            float dk = fmaxf(fmaxf(dsh_a[sc], dsh_a[sd]), fmaxf(dsh_b[sc], dsh_b[sd]));
-            dm = fmaxf(dm, 0.5f * dk);
-            if (qab * qcd * (double)dm < a.tau) continue;
+    // Warp-level compaction of the surviving kets: every warp scans 32 candidate kets at a time, applies the
+    // density-weighted screening, and queues the survivors in shared memory; the expensive part below always
+    // runs on (up to) 32 survivors, one per lane, so screened-out kets cost a scan step instead of an idle
+    // lane for a whole contracted quartet (lane utilisation was 21-25 of 32 without it).
+    __shared__ int ket_queue[4][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int qn = 0;
+    int scan = ket0 + warp * 32;
+    while (true) {
+        while (qn < 32 && scan < nket) {
+            const int ikc = scan + lane;
+            bool ok = ikc < nket;
+            if (ok && a.tau > 0.0) {
+                const double qcd = __ldg(ket.Q + ikc);
+                const int sc = __ldg(ket.sa + ikc), sd = __ldg(ket.sb + ikc);
+                float dm = fmaxf(dab, __ldg(a.Dsh + (size_t)sc * a.nshell + sd));
+                float dk = fmaxf(fmaxf(dsh_a[sc], dsh_a[sd]), fmaxf(dsh_b[sc], dsh_b[sd]));
+                dm = fmaxf(dm, 0.5f * dk);
+                ok = !(qab * qcd * (double)dm < a.tau);
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, ok);
+            if (ok) ket_queue[warp][qn + __popc(m & ((1u << lane) - 1u))] = ikc;
+            qn += __popc(m);
+            scan += blockDim.x;
         }
+        __syncwarp();
+        const int nrun = qn < 32 ? qn : 32;
+        if (nrun == 0) break;
+        if (lane < nrun) {
+        const int ik_ = ket_queue[warp][qn - nrun + lane];
+        const int sc = __ldg(ket.sa + ik_), sd = __ldg(ket.sb + ik_);
         ++nq;
         const int fc = __ldg(ket.fa + ik_), fd = __ldg(ket.fb + ik_);
         double deg = bra_deg * ((sc == sd) ? 0.5 : 1.0);
@@ -642,11 +664,13 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
                 for (int j = 0; j < ND; ++j) red_add(AK + (size_t)(fb + i) * N + fd + j, acc[KA::OFF_BD + i * ND + j]);
             }
         }
+        }   // lane < nrun
+        qn -= nrun;
+        __syncwarp();
     }
 
     // ---- J_ab: reduce over the CTA, one atomic per element ----
     __shared__ double red[4][NAB];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NAB; ++i) {
         const double s = warp_sum(jab[i]);
