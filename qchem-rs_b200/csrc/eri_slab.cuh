@@ -336,16 +336,35 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     for (int i = 0; i < NAB; ++i) jab[i] = 0.0;
     unsigned int nq = 0;
 
-    for (int ik_ = ket0 + ksub * 32 + lane; ik_ < nket; ik_ += 32 * NSUB) {
-        const double qcd = __ldg(ket.Q + ik_);
-        const int sc = __ldg(ket.sa + ik_), sd = __ldg(ket.sb + ik_);
-        if (a.tau > 0.0) {
-            float dm = fmaxf(dab, __ldg(a.Dsh + (size_t)sc * a.nshell + sd));
-            float dk = fmaxf(fmaxf(__ldg(a.Dsh + (size_t)sa * a.nshell + sc), __ldg(a.Dsh + (size_t)sa * a.nshell + sd)),
-                             fmaxf(__ldg(a.Dsh + (size_t)sb * a.nshell + sc), __ldg(a.Dsh + (size_t)sb * a.nshell + sd)));
-            dm = fmaxf(dm, 0.5f * dk);
-            if (qab * qcd * (double)dm < a.tau) continue;
+    // warp-level compaction of the surviving kets (see eri_jk_kernel): scan 32 candidates, queue the survivors,
+    // run the quartet work on full warps
+    __shared__ int ket_queue[NSUB][64];
+    int qn = 0;
+    int scan = ket0 + ksub * 32;
+    while (true) {
+        while (qn < 32 && scan < nket) {
+            const int ikc = scan + lane;
+            bool ok = ikc < nket;
+            if (ok && a.tau > 0.0) {
+                const double qcd = __ldg(ket.Q + ikc);
+                const int sc = __ldg(ket.sa + ikc), sd = __ldg(ket.sb + ikc);
+                float dm = fmaxf(dab, __ldg(a.Dsh + (size_t)sc * a.nshell + sd));
+                float dk = fmaxf(fmaxf(__ldg(a.Dsh + (size_t)sa * a.nshell + sc), __ldg(a.Dsh + (size_t)sa * a.nshell + sd)),
+                                 fmaxf(__ldg(a.Dsh + (size_t)sb * a.nshell + sc), __ldg(a.Dsh + (size_t)sb * a.nshell + sd)));
+                dm = fmaxf(dm, 0.5f * dk);
+                ok = !(qab * qcd * (double)dm < a.tau);
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, ok);
+            if (ok) ket_queue[ksub][qn + __popc(m & ((1u << lane) - 1u))] = ikc;
+            qn += __popc(m);
+            scan += 32 * NSUB;
         }
+        __syncwarp();
+        const int nrun = qn < 32 ? qn : 32;
+        if (nrun == 0) break;
+        if (lane < nrun) {
+        const int ik_ = ket_queue[ksub][qn - nrun + lane];
+        const int sc = __ldg(ket.sa + ik_), sd = __ldg(ket.sb + ik_);
         if (sg == 0) ++nq;
         const int fc = __ldg(ket.fa + ik_), fd = __ldg(ket.fb + ik_);
         double deg = bra_deg * ((sc == sd) ? 0.5 : 1.0);
@@ -384,6 +403,9 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
             }
             slab_digest<LA, LB, LC, LD, NK, SPT>(sg, Hs, tb + EL::E3_OFF, pab_s, jab_s, jab, a, fa, fb, fc, fd);
         }
+        }   // lane < nrun
+        qn -= nrun;
+        __syncwarp();
     }
 
     // ---- J_ab: reduce over the CTA, one atomic per element ----
