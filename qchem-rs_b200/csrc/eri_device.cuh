@@ -37,8 +37,8 @@ __host__ __device__ constexpr int hidx(int t, int u, int v) {
 // ---- pair data layout --------------------------------------------------------------------------
 // One "pair group" = all significant shell pairs of one (la >= lb) class with the same number of
 // primitive pairs K, sorted by power-of-two Schwarz bucket (descending) and, inside a bucket, by shell
-// indices, so that neighbouring lanes gather/scatter neighbouring density and Fock elements.  Structure of arrays: field f of primitive
-// k of pair i sits at prim[(k * PF_COUNT + f) * npair + i], so consecutive kets (= consecutive lanes)
+// indices, so that neighbouring lanes gather/scatter neighbouring density and Fock elements.
+// Structure of arrays: field f of primitive k of pair i sits at prim[(k * PF_COUNT + f) * npair + i], so consecutive kets (= consecutive lanes)
 // read consecutive doubles.
 enum PrimField { PF_P = 0, PF_PX, PF_PY, PF_PZ, PF_C, PF_PAX, PF_PAY, PF_PAZ, PF_COUNT };
 struct PairGroup {
@@ -227,6 +227,8 @@ __device__ __forceinline__ void hermite_R(const double (&c)[L + 1], double X, do
 // Classes whose integral block does not fit the register file (LARGE) keep R (cube layout), the E
 // tables and the block in local memory (L1) and run ONE out-of-line slab function with runtime ket
 // component indices; all other classes are fully unrolled and inlined with compile-time indices.
+// (The Fock build serves every LARGE class with the slab kernel of eri_slab.cuh; this path remains for
+// the single-quartet parity kernel and the (dd|dd) Schwarz diagonal, which need the whole block at once.)
 template <int LA, int LB, int LC, int LD>
 struct ClassTraits {
     static constexpr int NI = ncart(LA) * ncart(LB) * ncart(LC) * ncart(LD);
@@ -547,7 +549,7 @@ __device__ __forceinline__ void digest_all(const double* __restrict__ I, double*
     }
 }
 
-// ---- the Fock-build kernel: one CTA per bra pair, threads stride over its surviving kets ---------
+// ---- the block Fock-build kernel: one CTA per (bra pair, chunk of its ket prefix); s/p/ds bras -------
 // NK = number of exchange densities (1: RHF / single-density J,K;  2: UHF alpha,beta).
 template <int LA, int LB, int LC, int LD, int NK>
 __global__ void __launch_bounds__(128)
