@@ -9,11 +9,16 @@ iteration `--scf-iters` of that system (not random: density-weighted screening i
   python bench.py --gpus N --steps K --warmup W            own arm (CUDA engine; torchrun for N > 1)
   python bench.py --impl reference ...                     the reference algorithm on the host cores
 
-`value`  : unique shell quartets evaluated per second, whole job, P resident in HBM.
-`e2e`    : same metric through the host API (P in pinned host memory -> H2D -> build -> allreduce -> D2H G, pinned).
+`value`  : unique shell quartets evaluated per second, whole job, P resident in HBM (one process per GPU, partial
+           matrices summed by one NCCL all-reduce).
+`e2e`    : same metric through the drop-in C-ABI call qcf_build_rhf with caller-owned HOST buffers (H2D of P and D2H of
+           G inside the timed region).  N > 1: ONE context created with n_gpus = N drives all GPUs from rank 0's single
+           host thread (in-library multi-GPU: peer copies of P, partial matrices summed over NVLink peer memory inside
+           the finalize kernel); the other ranks wait on a CPU barrier.
 `roofline`: SURVEY.md 8d model flops of the evaluated quartets / CUDA-event time / measured FP64 FMA peak.
 The oracle is used ONLY in the cpu_baseline / --impl reference legs (it is the CPU restatement of the
-reference; the reference itself needs cargo + the absent `molint` crate and cannot be built).
+reference; the reference itself needs cargo + the absent `molint` crate and cannot be built).  The reference arm
+never imports the CUDA engine: its density comes from a committed fixture (tests/golden/) or the Hueckel guess.
 """
 from __future__ import annotations
 
@@ -35,6 +40,7 @@ import qcpkg  # noqa: E402
 
 METRIC = "fock_build_shell_quartets_per_s"
 UNIT = "quartets/s"
+GOLD = ROOT / "tests" / "golden"
 
 
 def parse():
@@ -48,6 +54,8 @@ def parse():
     ap.add_argument("--tau", type=float, default=1e-12)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--deterministic", action="store_true", help="time the fixed-point (bitwise reproducible) mode")
+    ap.add_argument("--scf", action="store_true", help="also time a whole device-resident SCF (reported in config.scf)")
     return ap.parse_args()
 
 
@@ -99,17 +107,22 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def hbm_note():
-    """DRAM side of the roofline for the largest launch of the top class, (ps|ss) K = 3x3, from the committed
-    ncu --set full capture (profiles/r1_final_block_kernel_1000.txt): 6.39 MB read+written in 0.588 ms."""
-    peak = 6524.3
+def measured_hbm_peak():
     try:
-        peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+        return float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]), "measured"
     except Exception:
-        pass
-    achieved = 6.39e6 / 0.588e-3 / 1e9
-    return {"achieved_gbs": achieved, "peak_gbs": peak, "frac": achieved / peak,
-            "source": "ncu capture in profiles/ (not measured live); the path is FP64-pipe bound, not HBM bound"}
+        return 6650.0, "fallback"
+
+
+def ncu_traffic():
+    """dram read+write bytes per launch of the dominant kernel from this round's ncu --set full capture, if the summary
+    was committed (profiles/r2_roofline_traffic.json); None otherwise -- never a typed-in constant."""
+    f = ROOT / "profiles" / "r2_roofline_traffic.json"
+    try:
+        doc = json.loads(f.read_text())
+        return float(doc["dram_bytes_per_launch"]), doc.get("kernel"), str(f.relative_to(ROOT))
+    except Exception:
+        return None, None, None
 
 
 def scf_density(pkg, system, ints, builder, iters):
@@ -125,9 +138,21 @@ def scf_density(pkg, system, ints, builder, iters):
     return seen["P"], out
 
 
-def cpu_sample(pkg, fb, P, tau, budget_s):
+def fixture_path(waters, iters):
+    return GOLD / f"waters{waters}_scf{iters}_density_factor.npz"
+
+
+def load_fixture_density(waters, iters):
+    """P = L L^T from the committed rank-n_occ factor of the SCF-iteration density (tools/make_bench_density.py)."""
+    f = fixture_path(waters, iters)
+    if not f.exists():
+        return None
+    L = np.load(f)["L"]
+    return L @ L.T
+
+
+def cpu_sample(fb, P, tau, budget_s, oracle_lib):
     """Oracle direct-SCF Fock build (OpenMP) on a bounded sample: every `stride`-th bra pair."""
-    from oracle import oracle_lib
     d = oracle_lib.DirectFock(fb, tau=tau)
     ncores = oracle_lib.num_threads()
     npair = len(fb.shell_l) * (len(fb.shell_l) + 1) // 2
@@ -144,39 +169,65 @@ def cpu_sample(pkg, fb, P, tau, budget_s):
             "seconds_per_iter_extrapolated": (t1 - t0) * stride}
 
 
+def ref_faithful_leg(pkg, oracle_lib, gpu_engine_cls=None):
+    """SURVEY.md 8d-(1) / BASELINE.md 3: the reference's own algorithm, single thread like the reference -- the one-off
+    N^4 ERI tensor (molint::eri, rhf.rs:45), the repack (rhf.rs:58-62, inside the first contraction) and the per-iteration
+    dense contraction (rhf.rs:152-167) -- on benzene / 6-31G (N = 66, the largest BASELINE config the reference's 8 N^4
+    bytes allow in seconds), with the GPU build of the same molecule beside it."""
+    bs = pkg.BasisSet.load(ROOT / "data" / "basis" / "6-31G.json")
+    system = pkg.MolecularSystem.load(ROOT / "data" / "mol" / "benzene.json", bs)
+    fb = system.flat()
+    n = fb.n_basis
+    nthreads = oracle_lib.num_threads()
+    oracle_lib.set_num_threads(1)
+    try:
+        t0 = time.perf_counter(); dense = oracle_lib.DenseFock(fb); t1 = time.perf_counter()
+        rng = np.random.default_rng(0)
+        a = rng.normal(size=(n, n)); P = 0.5 * (a + a.T)
+        dense.rhf(P)                                   # builds ET (rhf.rs:58-62) on the first call
+        t2 = time.perf_counter(); dense.rhf(P); t3 = time.perf_counter()
+    finally:
+        oracle_lib.set_num_threads(nthreads)
+    out = {"config": f"benzene 6-31G RHF, N={n}", "threads": 1, "eri_tensor_build_s": t1 - t0,
+           "contraction_s_per_iter": t3 - t2, "tensor_bytes": 8 * n ** 4}
+    if gpu_engine_cls is not None:
+        with gpu_engine_cls(system, tau=1e-12) as eng:
+            for _ in range(3):
+                eng.rhf(P)
+            st = eng.stats()
+            out["gpu_build_ms"] = st["kernel_ms"]
+            out["gpu_e2e_ms"] = st["total_ms"]
+            out["gpu_create_ms"] = st["create_ms"]
+    return out
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port, direct-SCF form, all host threads)."""
+    """--impl reference: the reference's CPU algorithm (oracle port, direct-SCF form, all host threads).  This arm never
+    imports the CUDA engine."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     pkg = qcpkg.load()
     from oracle import oracle_lib
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: use the host's cores explicitly so that the CPU arm is the same
+    # at every --gpus N
+    ncores = os.cpu_count() or oracle_lib.num_procs()
+    oracle_lib.set_num_threads(ncores)
     bs = pkg.BasisSet.load(ROOT / "data" / "basis" / "6-31G_st.json")
     system = pkg.MolecularSystem.from_atoms(pkg.molecules.water_cluster(args.waters), bs)
     fb = system.flat()
     n = fb.n_basis
-    # density: superposition-free cheap stand-in is not allowed to differ from the own arm's workload, so
-    # use the same SCF-iteration density when the CUDA engine is available; otherwise the Hueckel guess.
-    ints = oracle_lib.one_electron(fb)
-    P = None
-    try:
-        import torch
-        if torch.cuda.is_available():
-            with pkg.engine.FockEngine(system, tau=args.tau) as eng:
-                P, _ = scf_density(pkg, system, ints, eng, args.scf_iters)
-    except Exception:
-        P = None
-    dens_note = f"SCF iteration {args.scf_iters}"
-    if P is None:
-        S, T, V = ints
+    P = load_fixture_density(args.waters, args.scf_iters)
+    dens_note = f"SCF iteration {args.scf_iters} density, committed fixture {fixture_path(args.waters, args.scf_iters).name}"
+    if P is None or P.shape != (n, n):
+        S, T, V = oracle_lib.one_electron(fb)
         x = pkg.hf.compute_transformation_matrix(S)
         P = pkg.hf.compute_hueckel_density(T + V, S, x, system.n_electrons() // 2, 2.0)
-        dens_note = "Hueckel guess (no CUDA device for the SCF pre-iterations)"
+        dens_note = "Hueckel guess density (no committed SCF-iteration fixture for this cluster size)"
     per_step = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
-    res = None
     times, quartets = [], []
     d = oracle_lib.DirectFock(fb, tau=args.tau)
-    probe = cpu_sample(pkg, fb, P, args.tau, per_step)
+    probe = cpu_sample(fb, P, args.tau, per_step, oracle_lib)
     stride = max(1, int(round(probe["seconds_per_iter_extrapolated"] / per_step)))
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter(); d.jk([P], stride=stride, offset=stride // 2); t1 = time.perf_counter()
@@ -184,16 +235,16 @@ def run_reference(args):
             times.append(t1 - t0); quartets.append(d.last_quartets)
     tot_t, tot_q = sum(times), sum(quartets)
     value = tot_q / tot_t
+    sample = (f"every {stride}-th bra shell pair per step (rate measured on a 1/{stride} sample of the same build and "
+              f"compared rate-to-rate; extrapolated full build {stride * tot_t / args.steps:.1f} s/iter)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": f"synthetic ({dens_note} density of a generated water cluster)",
-            "config": {"workload": workload_name(args.waters, n), "tau": args.tau,
-                       "sample": f"every {stride}-th bra shell pair per step"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle_lib.num_threads(), "kind": "port",
-                             "sample": f"every {stride}-th bra shell pair per step, {args.steps} steps, "
-                                       f"extrapolated full build {stride * tot_t / args.steps:.1f} s/iter"},
+            "vs_baseline": None, "dtype": "f64", "data": f"synthetic ({dens_note}; generated water cluster)",
+            "config": {"workload": workload_name(args.waters, n), "tau": args.tau, "sample": sample,
+                       "sampled": stride > 1, "seconds_per_full_build_extrapolated": stride * tot_t / args.steps},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle_lib.num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "engine_library_loaded": pkg.engine._LIB is not None}
     print(json.dumps(line), flush=True)
 
 
@@ -208,9 +259,11 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")     # CPU barriers while one rank drives all GPUs (e2e)
     if world != args.gpus and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
 
@@ -218,10 +271,12 @@ def run_b200(args):
     system = pkg.MolecularSystem.from_atoms(pkg.molecules.water_cluster(args.waters), bs)
     fb = system.flat()
     n = fb.n_basis
-    eng = pkg.engine.FockEngine(system, tau=args.tau, device=local, rank=rank, world_size=world)
+    eng = pkg.engine.FockEngine(system, tau=args.tau, device=local, rank=rank, world_size=world, deterministic=args.deterministic)
     fock = pkg.distributed.DeviceFock(eng, dev)
     ints = eng.one_electron()
     P, _ = scf_density(pkg, system, ints, fock, args.scf_iters)        # same on every rank (allreduced G)
+    fixture = load_fixture_density(args.waters, args.scf_iters)
+    fixture_diff = float(np.max(np.abs(fixture - P))) if fixture is not None and fixture.shape == P.shape else None
     fock.dP[0].copy_(torch.from_numpy(P))
     peak = eng.fp64_peak_tflops()
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # 512 MB > 126 MB L2
@@ -232,22 +287,31 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, stats_of, sync=True):
         for _ in range(warmup):
             fn()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        q = fl = 0
+        q = fl = host = 0.0
         launches = 0
-        barrier()
+        if sync:
+            barrier()
+        else:
+            torch.cuda.synchronize(dev)
         for e0, e1 in ev:
             flush.zero_()
             e0.record()
             fn()
             e1.record()
-            st = eng.stats()          # waits for the build; counters of this rank
-            q += st["quartets"]; fl += st["model_flops"]; launches += st["launches"]
-        barrier()
+            st = stats_of.stats()          # waits for the build; counters of this rank / context
+            q += st["quartets"]; fl += st["model_flops"]; launches += st["launches"]; host += st["host_ms"]
+        if sync:
+            barrier()
+        else:
+            torch.cuda.synchronize(dev)
         ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+        return ms, q, fl, launches, host
+
+    def reduce_over_ranks(ms, q, fl, launches):
         t = torch.tensor([ms, float(q), fl, float(launches)], dtype=torch.float64, device=dev)
         if world > 1:
             tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -257,39 +321,95 @@ def run_b200(args):
         return ms, q, fl, int(launches)
 
     with ClockSampler(local) as clk:
-        ms, q, fl, launches = timed(lambda: fock.rhf_device(), args.steps, args.warmup)
+        ms, q, fl, launches, host_ms = timed(lambda: fock.rhf_device(), args.steps, args.warmup, eng)
+    kernel_ms_rank = eng.stats()["kernel_ms"]
+    ms, q, fl, launches = reduce_over_ranks(ms, q, fl, launches)
     clocks = clk.summary()
-    # e2e: the density lives in pinned host memory (the engine's staging buffer); every step copies it to the
-    # device, builds, all-reduces and reads the Fock matrix back into pinned host memory
-    # (N = 1: the drop-in C-ABI call itself, qcf_build_rhf with caller-owned host buffers; N > 1: pinned buffers +
-    # NCCL all-reduce, since the C ABI leaves the reduction to the caller)
-    fock.hP[0].copy_(torch.from_numpy(P))
-    e2e_call = (lambda: eng.rhf(P)) if world == 1 else (lambda: fock.rhf_pinned())
-    ms_e, q_e, _, _ = timed(e2e_call, args.steps, max(1, args.warmup // 2))
+    rank_ms = [kernel_ms_rank]
+    if world > 1:
+        t = torch.zeros(world, dtype=torch.float64, device=dev); t[rank] = kernel_ms_rank
+        dist.all_reduce(t)
+        rank_ms = t.tolist()
+
+    # ---- e2e: the drop-in C-ABI call with HOST buffers ------------------------------------------------------------
+    st0 = eng.stats()
+    e2e = None
+    if world == 1:
+        ms_e, q_e, _, _, _ = timed(lambda: eng.rhf(P), args.steps, max(1, args.warmup // 2), eng)
+        e2e = {"value": q_e / (ms_e * 1e-3), "ms_per_step": ms_e / args.steps, "path": "qcf_build_rhf, one context, one GPU"}
+    else:
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            # one context, n_gpus = world, driven from this host thread; the other ranks idle on a CPU barrier
+            with pkg.engine.FockEngine(system, tau=args.tau, device=0, n_gpus=world, deterministic=args.deterministic) as eng_all:
+                ms_e, q_e, _, _, _ = timed(lambda: eng_all.rhf(P), args.steps, max(2, args.warmup // 2), eng_all, sync=False)
+                dev_ms = eng_all.device_times()
+                st_all = eng_all.stats()
+            e2e = {"value": q_e / (ms_e * 1e-3), "ms_per_step": ms_e / args.steps,
+                   "path": f"qcf_build_rhf, ONE context with n_gpus={world} in rank 0's process (single host thread)",
+                   "device_ms": dev_ms, "host_enqueue_ms": st_all["host_ms"], "create_ms": st_all["create_ms"],
+                   "rank_imbalance_model": st_all["rank_imbalance"]}
+        dist.barrier(group=cpu_group)
+
+    scf = None
+    if args.scf and rank == 0 and world == 1:
+        cfg = pkg.hf.HartreeFockConfig(60, 1e-6)
+        t0 = time.perf_counter(); out_dev = pkg.hf.restricted_hartree_fock_device(system, cfg, ints, eng); t1 = time.perf_counter()
+        t2 = time.perf_counter(); out_inc = pkg.hf.restricted_hartree_fock_device(system, cfg, ints, eng, full_rebuild_every=8); t3 = time.perf_counter()
+        scf = {"epsilon": 1e-6}
+        for name, o, dt in (("full_builds", out_dev, t1 - t0), ("incremental_every_8", out_inc, t3 - t2)):
+            if o is not None:
+                scf[name] = {"iterations": o.iterations, "wall_s": dt, "e_total": o.total_energy(),
+                             "build_ms": [round(s["build_ms"], 2) for s in o.steps],
+                             "linalg_ms_mean": float(np.mean([s["linalg_ms"] for s in o.steps]))}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_sample(pkg, fb, P, args.tau, args.cpu_seconds)
+        from oracle import oracle_lib
+        oracle_lib.set_num_threads(os.cpu_count() or 1)
+        cpu = cpu_sample(fb, P, args.tau, args.cpu_seconds, oracle_lib)
+        try:
+            cpu["ref_faithful"] = ref_faithful_leg(pkg, oracle_lib, pkg.engine.FockEngine)
+        except Exception as exc:       # the N^4 leg is a side report; never lose the headline line to it
+            cpu["ref_faithful"] = {"error": repr(exc)}
     if rank == 0:
         value = q / (ms * 1e-3)
         achieved = fl / (ms * 1e-3) / 1e12
+        hbm_peak, hbm_kind = measured_hbm_peak()
+        # algorithmic bytes of one build: pair data (8 doubles per kept primitive pair + ~64 B per pair), P in, G out, three accumulators
+        alg_bytes = 64.0 * st0["prim_pairs_kept"] + 64.0 * st0["n_pairs"] + 5 * 8.0 * n * n
+        traffic, traffic_kernel, traffic_src = ncu_traffic()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": f"synthetic (SCF iteration {args.scf_iters} density of a generated water cluster)",
-                "config": {"workload": workload_name(args.waters, n), "tau": args.tau, "parallelism": f"bra-pair split x{world}",
+                "config": {"workload": workload_name(args.waters, n), "tau": args.tau,
+                           "parallelism": f"cost-balanced bra-pair split x{world}",
                            "l2": "flushed between timed steps (512 MB memset)", "quartets_per_step": q / args.steps,
-                           "quartets_unscreened": eng.stats()["quartets_total"]},
-                "e2e": {"value": q_e / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n * n, "d2h_bytes_per_step": 8 * n * n,
-                        "ms_per_step": ms_e / args.steps},
+                           "quartets_unscreened": st0["quartets_total"], "prim_pairs": st0["prim_pairs"],
+                           "prim_pairs_kept": st0["prim_pairs_kept"], "shell_pairs": st0["n_pairs"],
+                           "create_s": st0["create_ms"] * 1e-3, "host_enqueue_ms_per_build": host_ms / args.steps,
+                           "graph_launches_per_build": st0["graph_launches"], "deterministic": bool(args.deterministic),
+                           "rank_kernel_ms": [round(x, 3) for x in rank_ms], "rank_imbalance_model": st0["rank_imbalance"],
+                           "density_fixture_maxdiff": fixture_diff},
                 "gpu_launches": launches,
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak * world, "unit": "TFLOP/s",
-                             "frac": achieved / (peak * world), "traffic": 6.39e6,
-                             "hbm": hbm_note(),
-                             "note": "achieved = SURVEY 8d model flops of the evaluated quartets / CUDA-event time, all eri_jk "
-                                     "launches of the step; peak = FP64 FMA microbenchmark measured in this run (MEASURED_PEAKS.json "
-                                     "has no FP64 figure; nominal 37.2); traffic = dram read+write bytes of the largest launch of the top class (ps|ss), "
-                                     "ncu --set full capture in profiles/r1_final_block_kernel_1000.txt: the path is not HBM-bound"},
+                             "frac": achieved / (peak * world), "traffic": traffic,
+                             "traffic_kernel": traffic_kernel, "traffic_source": traffic_src,
+                             "hbm": {"algorithmic_bytes_per_build": alg_bytes, "achieved_gbs": alg_bytes / (ms / args.steps * 1e-3) / 1e9,
+                                     "peak_gbs": hbm_peak, "peak_kind": hbm_kind,
+                                     "frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / hbm_peak},
+                             "note": "achieved = SURVEY 8d model flops of the evaluated quartets / CUDA-event time of the whole step "
+                                     "(all eri_jk launches); peak = FP64 FMA microbenchmark measured in this run (MEASURED_PEAKS.json "
+                                     "has no FP64 figure; nominal 37.2 TFLOP/s); hbm = algorithmic bytes of one build (pair data + P + G + "
+                                     "accumulators) / step time against the measured copy bandwidth: the path is FP64-pipe bound, not HBM bound; "
+                                     "traffic = dram bytes per launch of the dominant kernel from this round's ncu capture (null if none committed)"},
                 "clocks": clocks}
+        if e2e is not None:
+            e2e.update({"unit": UNIT, "h2d_bytes_per_step": 8 * n * n, "d2h_bytes_per_step": 8 * n * n})
+            line["e2e"] = e2e
+        if scf is not None:
+            line["config"]["scf"] = scf
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

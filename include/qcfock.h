@@ -48,13 +48,33 @@ typedef struct {
     int cartesian;             /* must be 1 (6d)                               */
 } qcf_basis;
 
+/* ---- Loaders: native stand-ins for `BasisSet::load(path)` and
+ * `MolecularSystem::load(path, &basis)` (qchem-cli/src/main.rs:76-77, 120-121).  Reads the reference's own
+ * data/basis/*.json (MolSSI BSE schema) and data/mol/*.json and produces the flat qcf_basis above (fused SP
+ * shells split, zero coefficients dropped, primitive normalisation folded in).  Pure host code.
+ * On failure the returned object (if any) carries the message: qcf_system_error(). */
+typedef struct qcf_system qcf_system;
+int qcf_system_load(const char* basis_json_path, const char* molecule_json_path, qcf_system** out);
+const qcf_basis* qcf_system_basis(const qcf_system* sys);       /* valid until qcf_system_free */
+int qcf_system_n_electrons(const qcf_system* sys);              /* sum of Z (rhf.rs:36)        */
+int qcf_system_n_basis(const qcf_system* sys);                  /* system.n_basis() (rhf.rs:37) */
+double qcf_system_nuclear_repulsion(const qcf_system* sys);     /* rhf.rs:110-122              */
+const char* qcf_system_error(const qcf_system* sys);
+void qcf_system_free(qcf_system* sys);
+
 typedef struct {
     double screen_tau; /* skip quartets with Q_ab Q_cd D_max < tau; <= 0 selects the default 1e-12;
                           QCF_TAU_NONE (any value < -0.5) disables screening entirely            */
-    int device;        /* CUDA device ordinal                                                    */
-    int rank;          /* this context evaluates bra pairs i with i % world_size == rank;         */
-    int world_size;    /*   the caller sums the partial results of all ranks (one allreduce)      */
+    int device;        /* first CUDA device ordinal of this context                               */
+    int rank;          /* multi-PROCESS use: this context evaluates share `rank` of `world_size`   */
+    int world_size;    /*   of the cost-balanced bra split; the caller sums the partial matrices   */
     int block_threads; /* 0 = default                                                             */
+    int n_gpus;        /* single-process multi-GPU: the context drives the devices  */
+                       /*   device .. device+n_gpus-1 from the calling host thread, replicates P, */
+                       /*   splits the bra list by modelled cost and sums the partial matrices     */
+                       /*   over NVLink peer memory inside the finalize kernel; 0 or 1 = one GPU   */
+    int deterministic; /* 1: fixed-point accumulation (64-bit integer atomics) and fixed-order     */
+                       /*   reductions -- results are bitwise reproducible from run to run         */
 } qcf_opts;
 #define QCF_TAU_NONE (-1.0)
 
@@ -68,6 +88,11 @@ typedef struct {
     int launches;              /* kernels launched by the last build                              */
     long long prim_pairs;      /* primitive pairs of all shell pairs before primitive screening    */
     long long prim_pairs_kept; /* ... and those the kernels loop over                               */
+    double create_ms;          /* wall time of qcf_create (pairs, Schwarz, upload, launch plan)     */
+    double host_ms;            /* host time the last build spent enqueueing work (no device waits) */
+    int n_devices;             /* GPUs driven by this context                                      */
+    int graph_launches;        /* CUDA-graph launches of the last build (0: stream launches)       */
+    double rank_imbalance;     /* max / mean modelled cost over the ranks of the bra split          */
 } qcf_stats_t;
 
 /* Build shell pairs, Schwarz bounds and the device-resident pair data.  (Replaces the one-off
@@ -82,10 +107,18 @@ int qcf_build_uhf(qcf_ctx* ctx, const double* Pa, const double* Pb, double* Ga, 
 /* J_d = sum_kl P_d,kl (ij|kl),  K_d = sum_kl P_d,kl (ik|jl)  for nd densities. */
 int qcf_build_jk(qcf_ctx* ctx, int nd, const double* const* P, double* const* J, double* const* K);
 
-/* Device-resident variants for multi-process runs: dP / dG are device pointers on the context's
- * device (N*N doubles each), the call is asynchronous on `stream` (a cudaStream_t, may be 0) and the
- * result is this rank's PARTIAL, already symmetrised, matrix -- sum it over ranks with one
- * allreduce (ncclAllReduce / torch.distributed.all_reduce). */
+/* Incremental (difference-density) builds: G = G_prev + G(P - P_prev), screened on the block maxima of
+ * P - P_prev, which shrink as the SCF converges.  The context keeps P_prev and G_prev on the device;
+ * `reset` != 0 (or the first call) starts from P_prev = 0, i.e. a full build.  Same result as
+ * qcf_build_rhf / qcf_build_uhf up to the screening threshold per build. */
+int qcf_build_rhf_incremental(qcf_ctx* ctx, const double* P, double* G, int reset);
+int qcf_build_uhf_incremental(qcf_ctx* ctx, const double* Pa, const double* Pb, double* Ga, double* Gb, int reset);
+
+/* Device-resident variants: dP / dG are device pointers on the context's first device (N*N doubles
+ * each); the call only ENQUEUES work on `stream` (a cudaStream_t of that device, may be 0) and returns
+ * without waiting for the device.  With world_size > 1 the result is this rank's PARTIAL, already
+ * symmetrised, matrix -- sum it over ranks with one allreduce (ncclAllReduce /
+ * torch.distributed.all_reduce); with n_gpus > 1 it is the complete matrix. */
 int qcf_build_rhf_dev(qcf_ctx* ctx, const double* dP, double* dG, void* stream);
 int qcf_build_uhf_dev(qcf_ctx* ctx, const double* dPa, const double* dPb, double* dGa, double* dGb, void* stream);
 
@@ -105,7 +138,35 @@ int qcf_boys(qcf_ctx* ctx, int mmax, int n, const double* T, double* F);
 /* Measured FP64 FMA peak of the context's device in TFLOP/s (dependent-chain microbenchmark). */
 int qcf_fp64_peak(qcf_ctx* ctx, double* tflops);
 
+/* ---- Device-resident SCF iteration -------------------------------------------------
+ * The per-iteration linear algebra of the reference's loops -- F = H + G, FPS - SPF, DIIS, X^T F X, the
+ * symmetric eigensolve, the density update, energy and convergence test (rhf.rs:66-104, uhf.rs:79-189,
+ * diis.rs:28-59, utils.rs:20-36) -- on the GPU (cuBLAS / cuSOLVER FP64), so that P and G never leave HBM
+ * between iterations.  Same quirks as the reference loop; see qchem-rs_b200/csrc/scf_device.cu.
+ *   qcf_scf_init : S, H = T + V (N x N, host); builds X = S^-1/2 and the Hueckel guess density on the device.
+ *                  unrestricted = 0: RHF with n_alpha doubly occupied orbitals (n_beta ignored);
+ *                  unrestricted = 1: UHF.  full_rebuild_every = 0: every build is a full build; k > 0:
+ *                  difference-density (incremental) builds with a full rebuild every k-th iteration.
+ *   qcf_scf_step : one iteration; `converged` is the reference's test (density_rms < epsilon).
+ *   qcf_scf_get  : what = 0 density, 1 Fock matrix, 2 G (N*N doubles), 3 orbital energies (N doubles). */
+typedef struct {
+    int iteration;             /* loop index of this step (rhf.rs:66)                                */
+    int converged;
+    double electronic_energy;  /* 1/2 tr(P_new (2H + G(P_old)))  (rhf.rs:84-85)                      */
+    double density_rms;        /* diagonal-only rms of the density change (rhf.rs:87-88; uhf.rs:137) */
+    double build_ms;           /* device time of the Fock build                                      */
+    double linalg_ms;          /* device time of everything else in the step                         */
+    double wall_ms;            /* host wall time of the step                                         */
+} qcf_scf_info;
+int qcf_scf_init(qcf_ctx* ctx, const double* S, const double* H, int unrestricted, int n_alpha, int n_beta,
+                 int full_rebuild_every);
+int qcf_scf_step(qcf_ctx* ctx, double epsilon, qcf_scf_info* out);
+int qcf_scf_get(qcf_ctx* ctx, int what, int spin, double* out);
+
 int qcf_stats(const qcf_ctx* ctx, qcf_stats_t* out);
+/* Device time (ms, CUDA events) each GPU of the context spent on its share of the last build; returns the
+ * number of devices (writes at most max_dev values). */
+int qcf_device_times(qcf_ctx* ctx, int max_dev, double* ms);
 
 /* Per-launch record of the last build: class (la lb|lc ld), primitive-pair counts, list lengths,
  * unique shell quartets evaluated, model flops per primitive quartet, and -- only when the context was

@@ -35,6 +35,7 @@ def lib():
         L.orc_nuclear_repulsion.restype = ctypes.c_double
         L.orc_jk_direct.restype = ctypes.c_longlong
         L.orc_num_threads.restype = ctypes.c_int
+        L.orc_num_procs.restype = ctypes.c_int
         _LIB = L
     return _LIB
 
@@ -146,5 +147,34 @@ class DirectFock:
         return Ja + Jb - Ka, Ja + Jb - Kb
 
 
+def jk_blocks_exact(fb, P, pairs):
+    """Exact, UNSCREENED J and K blocks for the shell pairs `pairs` = [(sa, sb), ...]:
+    J_ab = sum_cd P_cd (ab|cd), K_ab = sum_cd P_cd (ac|bd) over ALL c, d -- the reference's dense contraction
+    (rhf.rs:58-62, 152-167; uhf.rs:210-227) restricted to one shell block.  Returns two lists of (na, nb) arrays."""
+    nc = lambda l: (l + 1) * (l + 2) // 2
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    sa = np.ascontiguousarray([p[0] for p in pairs], dtype=np.int32)
+    sb = np.ascontiguousarray([p[1] for p in pairs], dtype=np.int32)
+    shapes = [(nc(int(fb.shell_l[a])), nc(int(fb.shell_l[b]))) for a, b in pairs]
+    tot = sum(x * y for x, y in shapes)
+    J = np.zeros(tot); K = np.zeros(tot)
+    ip = ctypes.POINTER(ctypes.c_int)
+    lib().orc_jk_blocks_exact(fb.ref(), _p(P), ctypes.c_int(len(pairs)), sa.ctypes.data_as(ip), sb.ctypes.data_as(ip), _p(J), _p(K))
+    outJ, outK, o = [], [], 0
+    for x, y in shapes:
+        outJ.append(J[o:o + x * y].reshape(x, y).copy()); outK.append(K[o:o + x * y].reshape(x, y).copy()); o += x * y
+    return outJ, outK
+
+
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+def num_procs() -> int:
+    return lib().orc_num_procs()
+
+
+def set_num_threads(n: int) -> None:
+    """OpenMP thread count of the oracle.  torchrun exports OMP_NUM_THREADS=1 to its workers; bench.py's reference
+    arm calls this with the host's core count so that the CPU arm uses the same cores at every --gpus N."""
+    lib().orc_set_num_threads(ctypes.c_int(int(n)))

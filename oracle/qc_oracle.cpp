@@ -161,6 +161,12 @@ std::vector<Comp> components(int l) {
     return c;
 }
 
+// cached per l (components() allocates; the quartet routine is called ~1e7 times in the size-parity tests)
+const std::vector<Comp>& components_cached(int l) {
+    static const std::vector<Comp> tab[LMAX + 1] = {components(0), components(1), components(2), components(3)};
+    return tab[l];
+}
+
 struct ShellView {
     int l, nprim; const double* exps; const double* coefs; double A[3];
 };
@@ -181,7 +187,7 @@ std::vector<int> offsets(const orc_basis* b) {
 
 // Contracted ERI block (ab|cd), out[na][nb][nc][nd] row-major, chemists' notation.
 void eri_quartet(const ShellView& A, const ShellView& B, const ShellView& C, const ShellView& D, double* out) {
-    const auto ca = components(A.l), cb = components(B.l), cc = components(C.l), cd = components(D.l);
+    const auto &ca = components_cached(A.l), &cb = components_cached(B.l), &cc = components_cached(C.l), &cd = components_cached(D.l);
     const int na = ca.size(), nb = cb.size(), nc = cc.size(), nd = cd.size();
     std::fill(out, out + (size_t)na * nb * nc * nd, 0.0);
     const int L = A.l + B.l + C.l + D.l;
@@ -521,6 +527,73 @@ long long orc_jk_direct(const orc_basis* b, double tau, int nd, const double* co
             for (size_t i = 0; i < N * N; ++i) { J[d][i] += Jl[d][i]; K[d][i] += Kl[d][i]; }
     }
     return nq;
+}
+
+// Exact, UNSCREENED blocks of J and K for chosen shell pairs (sa[i], sb[i]):
+//   J_ab = sum_{cd} P_cd (ab|cd),   K_ab = sum_{cd} P_cd (ac|bd)      (all c, d -- nothing is skipped)
+// i.e. the reference's dense contraction (rhf.rs:58-62 + 152-167, uhf.rs:210-227) restricted to the rows/columns of
+// one shell block.  This is how parity is checked at sizes where neither the N^4 tensor (554 GB at N = 513) nor a
+// full unscreened direct build (1e10 quartets at N = 1007) is affordable: ~n_shell^2 quartets per block.
+// Blocks are written back to back, row-major [na][nb], in the order of the pair list.
+void orc_jk_blocks_exact(const orc_basis* b, const double* P, int npairs, const int* sa_list, const int* sb_list,
+                         double* J, double* K) {
+    const auto off = offsets(b);
+    const size_t N = off.back();
+    const int ns = b->n_shells;
+    std::vector<size_t> boff(npairs + 1, 0);
+    for (int i = 0; i < npairs; ++i)
+        boff[i + 1] = boff[i] + (size_t)ncart(b->shell_l[sa_list[i]]) * ncart(b->shell_l[sb_list[i]]);
+    std::fill(J, J + boff[npairs], 0.0);
+    std::fill(K, K + boff[npairs], 0.0);
+    const long long work = (long long)npairs * ns;
+    #pragma omp parallel
+    {
+        std::vector<double> blk((size_t)ncart(LMAX) * ncart(LMAX) * ncart(LMAX) * ncart(LMAX));
+        std::vector<double> jl(ncart(LMAX) * ncart(LMAX)), kl(ncart(LMAX) * ncart(LMAX));
+        #pragma omp for schedule(dynamic, 4)
+        for (long long w = 0; w < work; ++w) {
+            const int ip = (int)(w / ns), sc = (int)(w % ns);
+            const int sa = sa_list[ip], sb = sb_list[ip];
+            ShellView A = shell(b, sa), B = shell(b, sb), C = shell(b, sc);
+            const int na = ncart(A.l), nb = ncart(B.l), nc = ncart(C.l);
+            std::fill(jl.begin(), jl.end(), 0.0);
+            std::fill(kl.begin(), kl.end(), 0.0);
+            for (int sd = 0; sd < ns; ++sd) {
+                ShellView D = shell(b, sd);
+                const int nd = ncart(D.l);
+                if (sd <= sc) {   // Coulomb: (ab|cd), unordered shell pair {c,d} once, weight 2 off the diagonal
+                    eri_quartet(A, B, C, D, blk.data());
+                    const double wgt = sd == sc ? 1.0 : 2.0;
+                    size_t idx = 0;
+                    for (int i = 0; i < na; ++i) for (int j = 0; j < nb; ++j)
+                    for (int k = 0; k < nc; ++k) for (int l = 0; l < nd; ++l, ++idx)
+                        jl[i * nb + j] += wgt * P[(off[sc] + k) + (off[sd] + l) * N] * blk[idx];
+                }
+                // exchange: (ac|bd)
+                eri_quartet(A, C, B, D, blk.data());
+                size_t idx = 0;
+                for (int i = 0; i < na; ++i) for (int k = 0; k < nc; ++k)
+                for (int j = 0; j < nb; ++j) for (int l = 0; l < nd; ++l, ++idx)
+                    kl[i * nb + j] += P[(off[sc] + k) + (off[sd] + l) * N] * blk[idx];
+            }
+            #pragma omp critical
+            for (int i = 0; i < na * nb; ++i) { J[boff[ip] + i] += jl[i]; K[boff[ip] + i] += kl[i]; }
+        }
+    }
+}
+
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
+int orc_num_procs() {
+#ifdef _OPENMP
+    return omp_get_num_procs();
+#else
+    return 1;
+#endif
 }
 
 int orc_num_threads() {

@@ -38,39 +38,83 @@ constexpr bool USE_SLAB = QCF_USE_SLAB;
 constexpr bool USE_SLAB = (LA == 2 && LB >= 1);   // every dp- and dd-bra class
 #endif
 
+// lanes per shell quartet the block kernel of this class is compiled for (highly contracted launches; the d
+// shells of the supported basis sets are uncontracted or nearly so, so 8 is only built for the s/p bras)
+constexpr int MAX_PS = USE_SLAB ? 1 : (LA <= 1 ? 8 : 4);
+
 template <int NK>
 void launch_slab(int nbra, int nket_max, int kpt, cudaStream_t s, const PairGroup& bra, const PairGroup& ket, BuildArgs a, int same) {
     if constexpr (USE_SLAB) {
         using C = SlabCfg<LA, LB, LC, LD, NK, SPT>;
         auto kern = eri_jk_slab_kernel<LA, LB, LC, LD, NK, SPT>;
         const size_t smem = slab_smem_bytes<LA, LB, LC, LD, NK, SPT>(bra.K);
-        // opt in to more than 48 KB of dynamic shared memory (per device and per function, so it is not cached in
-        // a process-wide flag: one process may hold contexts on several devices)
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         a.ket_chunk = 32 * C::NSUB * kpt;
         const dim3 grid(nbra, (nket_max + a.ket_chunk - 1) / a.ket_chunk, C::G);
         kern<<<grid, C::BLOCK, smem, s>>>(bra, ket, a, same);
     }
 }
 
-void launch_jk(int nk, int nbra, int nket_max, int block, int kpt, cudaStream_t s, const PairGroup& bra, const PairGroup& ket,
-               const BuildArgs& a0, int same) {
-    BuildArgs a = a0;
+inline size_t block_smem_bytes(int braK, int nshell) {
+    // staged bra primitives + two rows of the shell-block density maxima
+    return (size_t)braK * BRA_S * sizeof(double) + 2 * (size_t)nshell * sizeof(float);
+}
+
+template <int NK, int PS>
+void launch_block(int nbra, int nket_max, int block, int kpt, cudaStream_t s, const PairGroup& bra, const PairGroup& ket, BuildArgs a, int same) {
+    if constexpr (!USE_SLAB && PS <= MAX_PS) {
+        // candidates per CTA: kpt per thread, spread over PS lanes each; at least one full scan step per warp
+        a.ket_chunk = block * kpt / PS;
+        const int min_chunk = block * BlockCfg<PS>::SW;
+        if (a.ket_chunk < min_chunk) a.ket_chunk = min_chunk;
+        const dim3 grid(nbra, (nket_max + a.ket_chunk - 1) / a.ket_chunk);
+        eri_jk_kernel<LA, LB, LC, LD, NK, PS><<<grid, block, block_smem_bytes(bra.K, a.nshell), s>>>(bra, ket, a, same);
+    }
+}
+
+void launch_jk(int nk, int ps, int nbra, int nket_max, int block, int kpt, cudaStream_t s, const PairGroup& bra, const PairGroup& ket,
+               const BuildArgs& a, int same) {
     if constexpr (USE_SLAB) {
         if (nk == 1) launch_slab<1>(nbra, nket_max, kpt, s, bra, ket, a, same);
         else launch_slab<2>(nbra, nket_max, kpt, s, bra, ket, a, same);
     } else {
-        a.ket_chunk = block * kpt;
-        const dim3 grid(nbra, (nket_max + a.ket_chunk - 1) / a.ket_chunk);
-        // dynamic shared memory: staged bra primitives + two rows of the shell-block density maxima
-        const size_t smem = (size_t)bra.K * BRA_S * sizeof(double) + 2 * (size_t)a.nshell * sizeof(float);
-        if (smem > 48 * 1024) {
-            if (nk == 1) cudaFuncSetAttribute(eri_jk_kernel<LA, LB, LC, LD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            else cudaFuncSetAttribute(eri_jk_kernel<LA, LB, LC, LD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ps > MAX_PS) ps = MAX_PS;
+        if (nk == 1) {
+            if (ps >= 8) launch_block<1, 8>(nbra, nket_max, block, kpt, s, bra, ket, a, same);
+            else if (ps >= 4) launch_block<1, 4>(nbra, nket_max, block, kpt, s, bra, ket, a, same);
+            else launch_block<1, 1>(nbra, nket_max, block, kpt, s, bra, ket, a, same);
+        } else {
+            if (ps >= 8) launch_block<2, 8>(nbra, nket_max, block, kpt, s, bra, ket, a, same);
+            else if (ps >= 4) launch_block<2, 4>(nbra, nket_max, block, kpt, s, bra, ket, a, same);
+            else launch_block<2, 1>(nbra, nket_max, block, kpt, s, bra, ket, a, same);
         }
-        if (nk == 1) eri_jk_kernel<LA, LB, LC, LD, 1><<<grid, block, smem, s>>>(bra, ket, a, same);
-        else eri_jk_kernel<LA, LB, LC, LD, 2><<<grid, block, smem, s>>>(bra, ket, a, same);
     }
+}
+
+// Opt in (once per device, at qcf_create) to the dynamic shared memory of the largest launch of this class.
+template <class K>
+cudaError_t set_smem(K kern, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+cudaError_t class_init(int max_bra_K, int nshell) {
+    cudaError_t e = cudaSuccess;
+    if constexpr (USE_SLAB) {
+        e = set_smem(eri_jk_slab_kernel<LA, LB, LC, LD, 1, SPT>, slab_smem_bytes<LA, LB, LC, LD, 1, SPT>(max_bra_K));
+        if (e == cudaSuccess) e = set_smem(eri_jk_slab_kernel<LA, LB, LC, LD, 2, SPT>, slab_smem_bytes<LA, LB, LC, LD, 2, SPT>(max_bra_K));
+    } else {
+        const size_t b = block_smem_bytes(max_bra_K, nshell);
+        e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 1>, b);
+        if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 2, 1>, b);
+        if constexpr (MAX_PS >= 4) {
+            if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 4>, b);
+            if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 2, 4>, b);
+        }
+        if constexpr (MAX_PS >= 8) {
+            if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 8>, b);
+            if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 2, 8>, b);
+        }
+    }
+    return e;
 }
 void launch_quartet(cudaStream_t s, const PairGroup& bra, int ib_, const PairGroup& ket, int ik_, const double* boys, double* out) {
     quartet_kernel<LA, LB, LC, LD><<<1, 32, 0, s>>>(bra, ib_, ket, ik_, boys, out);
@@ -85,7 +129,7 @@ void launch_schwarz(int grid, int block, cudaStream_t s, const PairGroup& g, con
 #define QCF_CAT2(a, b, c, d) qcf_class_##a##b##c##d
 #define QCF_CAT(a, b, c, d) QCF_CAT2(a, b, c, d)
 extern "C" const ClassLaunch QCF_CAT(QCF_LA, QCF_LB, QCF_LC, QCF_LD) = {
-    launch_jk, launch_quartet,
+    launch_jk, class_init, MAX_PS, launch_quartet,
 #if QCF_LA == QCF_LC && QCF_LB == QCF_LD
     launch_schwarz
 #else

@@ -52,6 +52,16 @@ struct PairGroup {
     const double* Qb;     // power-of-two bucket ceiling of Q, non-increasing along the list (prefix search)
     const double* prim;   // [K][PF_COUNT][npair];  PF_C = sqrt(2) pi^(5/4) c_a c_b exp(-mu AB^2) / p
     const double* AB;     // [3][npair]  A - B
+    const float* Dp;      // [npair] max |P| over the pair's shell block, rewritten by every build (pair_dmax_kernel)
+};
+
+// Per-build scalars that live on the device, so that a build never has to wait for the host:
+// the global density maximum (float bits, written by atomicMax) and the fixed-point scale of the deterministic mode.
+struct BuildScalars {
+    unsigned int dmax_bits;
+    unsigned int pad;
+    double fx_scale;          // 0: FP64 atomics (unordered);  > 0: accumulate round(v * fx_scale) with 64-bit integer atomics
+    double abs_sum;           // sum |P| (fixed-order reduction), the bound the scale is derived from
 };
 
 struct BuildArgs {
@@ -63,10 +73,11 @@ struct BuildArgs {
     double* AK0;
     double* AK1;
     const float* Dsh;         // [nshell][nshell] max |P| per shell block (over all densities)
-    double tau, dmax;         // screening threshold, global max of Dsh
+    double tau;               // screening threshold (0: no screening)
+    const BuildScalars* sc;   // device-resident per-build scalars (global density maximum, fixed-point scale)
     unsigned long long* counter;  // evaluated quartets of this launch
     const double* boys;       // [BOYS_LTOT+1][BOYS_NGRID][BOYS_ROW]
-    int rank, world;
+    const int* bra_list;      // this rank's share of the bra list (cost-balanced split); null: every bra pair
     int ket_chunk;            // kets per CTA (grid.y strides over the ket list)
 };
 
@@ -418,11 +429,15 @@ __device__ __forceinline__ void load_prim_staged(const double* __restrict__ b, d
         E.ax[0].e[0] = 1.0; E.ax[1].e[0] = 1.0; E.ax[2].e[0] = 1.0;
     }
 }
-// contracted quartet block with the bra primitives read from the staged copy
-template <int LA, int LB, int LC, int LD>
+// contracted quartet block with the bra primitives read from the staged copy.
+// PS > 1: PS consecutive lanes share this quartet; lane `sub` takes the primitive quartets sub, sub + PS, ... of the
+// flattened (ket primitive, bra primitive) loop and the partial blocks are summed over the lane group afterwards
+// (highly contracted classes: up to 36 x 36 primitive quartets per shell quartet would otherwise run serially in
+// one thread while few such quartets exist -- a latency tail).
+template <int LA, int LB, int LC, int LD, int PS>
 __device__ __forceinline__ void contracted_quartet_staged(const double* __restrict__ bra_s, int nkb, double ABx, double ABy, double ABz,
                                                           const PairGroup& ket, int ik_, double scale,
-                                                          const double* __restrict__ boys_table,
+                                                          const double* __restrict__ boys_table, int sub, unsigned int amask,
                                                           double (&I)[ncart(LA) * ncart(LB) * ncart(LC) * ncart(LD)]) {
     constexpr int NI = ncart(LA) * ncart(LB) * ncart(LC) * ncart(LD);
 #pragma unroll
@@ -432,22 +447,53 @@ __device__ __forceinline__ void contracted_quartet_staged(const double* __restri
         CDx = __ldg(ket.AB + ik_); CDy = __ldg(ket.AB + ket.npair + ik_); CDz = __ldg(ket.AB + 2 * (size_t)ket.npair + ik_);
     }
     const int nkc = __ldg(ket.nprim + ik_);
-    for (int kc = 0; kc < nkc; ++kc) {
-        double q, Qx, Qy, Qz, cQ;
-        PairE<LC, LD> Ecd;
-        load_prim<LC, LD>(ket, ik_, kc, CDx, CDy, CDz, q, Qx, Qy, Qz, cQ, Ecd, true);
-        cQ *= scale;
-        for (int kb = 0; kb < nkb; ++kb) {
-            double p, Px, Py, Pz, cP;
-            PairE<LA, LB> Eab;
-            load_prim_staged<LA, LB>(bra_s + kb * BRA_S, ABx, ABy, ABz, p, Px, Py, Pz, cP, Eab);
-            prim_quartet<LA, LB, LC, LD>(Eab, Ecd, p, q, Px - Qx, Py - Qy, Pz - Qz, cP * cQ, boys_table, I);
+    if constexpr (PS == 1) {
+        for (int kc = 0; kc < nkc; ++kc) {
+            double q, Qx, Qy, Qz, cQ;
+            PairE<LC, LD> Ecd;
+            load_prim<LC, LD>(ket, ik_, kc, CDx, CDy, CDz, q, Qx, Qy, Qz, cQ, Ecd, true);
+            cQ *= scale;
+            for (int kb = 0; kb < nkb; ++kb) {
+                double p, Px, Py, Pz, cP;
+                PairE<LA, LB> Eab;
+                load_prim_staged<LA, LB>(bra_s + kb * BRA_S, ABx, ABy, ABz, p, Px, Py, Pz, cP, Eab);
+                prim_quartet<LA, LB, LC, LD>(Eab, Ecd, p, q, Px - Qx, Py - Qy, Pz - Qz, cP * cQ, boys_table, I);
+            }
+        }
+    } else {
+        int kc = sub / nkb, kb = sub - kc * nkb;
+        while (kc < nkc) {
+            double q, Qx, Qy, Qz, cQ;
+            PairE<LC, LD> Ecd;
+            load_prim<LC, LD>(ket, ik_, kc, CDx, CDy, CDz, q, Qx, Qy, Qz, cQ, Ecd, true);
+            cQ *= scale;
+            for (; kb < nkb; kb += PS) {
+                double p, Px, Py, Pz, cP;
+                PairE<LA, LB> Eab;
+                load_prim_staged<LA, LB>(bra_s + kb * BRA_S, ABx, ABy, ABz, p, Px, Py, Pz, cP, Eab);
+                prim_quartet<LA, LB, LC, LD>(Eab, Ecd, p, q, Px - Qx, Py - Qy, Pz - Qz, cP * cQ, boys_table, I);
+            }
+            do { kb -= nkb; ++kc; } while (kb >= nkb);
+        }
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+#pragma unroll
+            for (int o = PS / 2; o > 0; o >>= 1) I[i] += __shfl_xor_sync(amask, I[i], o);
         }
     }
 }
 
-__device__ __forceinline__ void red_add(double* addr, double v) {
-    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+// Accumulation into the global J / K matrices.  fx == 0: red.global.add.f64 (summation order = arrival order, results
+// differ in the last bits from run to run).  fx > 0 (deterministic mode): the contribution is rounded to a multiple of
+// 1/fx and added with a 64-bit INTEGER atomic -- integer addition is associative, so the result is bitwise independent
+// of the arrival order; the finalize kernel converts back.
+__device__ __forceinline__ void red_add(double* addr, double v, double fx) {
+    if (fx != 0.0) {
+        const long long q = __double2ll_rn(v * fx);
+        atomicAdd(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)q);
+    } else {
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+    }
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -469,7 +515,7 @@ struct KAcc {
 
 template <int LA, int LB, int LC, int LD, int NK>
 __device__ __forceinline__ void digest_slab_impl(const double* __restrict__ I, double* __restrict__ jab,
-                                                 const double* __restrict__ pab, const BuildArgs& a, int fa, int fb,
+                                                 const double* __restrict__ pab, const BuildArgs& a, const double fx, int fa, int fb,
                                                  int fc, int fd, double* __restrict__ kacc, const int IC, const int ID) {
     using KA = KAcc<LA, LB, LC, LD>;
     constexpr int NA = KA::NA, NB = KA::NB, NC = KA::NC, ND = KA::ND;
@@ -485,7 +531,7 @@ __device__ __forceinline__ void digest_slab_impl(const double* __restrict__ I, d
             jab[iab] = fma(v, pcd, jab[iab]);
             s = fma(v, pab[iab], s);
         }
-        red_add(a.AJ + (size_t)(fc + IC) * N + fd + ID, s);
+        red_add(a.AJ + (size_t)(fc + IC) * N + fd + ID, s, fx);
     }
 #pragma unroll
     for (int kk = 0; kk < NK; ++kk) {
@@ -528,56 +574,116 @@ __device__ __forceinline__ void digest_slab_impl(const double* __restrict__ I, d
 }
 template <int LA, int LB, int LC, int LD, int NK>
 __device__ __noinline__ void digest_slab_call(const double* __restrict__ I, double* __restrict__ jab,
-                                              const double* __restrict__ pab, const BuildArgs& a, int fa, int fb, int fc,
+                                              const double* __restrict__ pab, const BuildArgs& a, double fx, int fa, int fb, int fc,
                                               int fd, double* __restrict__ kacc, int ic, int id) {
-    digest_slab_impl<LA, LB, LC, LD, NK>(I, jab, pab, a, fa, fb, fc, fd, kacc, ic, id);
+    digest_slab_impl<LA, LB, LC, LD, NK>(I, jab, pab, a, fx, fa, fb, fc, fd, kacc, ic, id);
 }
 template <int LA, int LB, int LC, int LD, int NK>
 __device__ __forceinline__ void digest_all(const double* __restrict__ I, double* __restrict__ jab, const double* __restrict__ pab,
-                                           const BuildArgs& a, int fa, int fb, int fc, int fd, double* __restrict__ kacc) {
+                                           const BuildArgs& a, double fx, int fa, int fb, int fc, int fd, double* __restrict__ kacc) {
     constexpr int NC = ncart(LC), ND = ncart(LD);
     if constexpr (ClassTraits<LA, LB, LC, LD>::LARGE) {
 #pragma unroll 1
         for (int ic = 0; ic < NC; ++ic)
 #pragma unroll 1
-            for (int id = 0; id < ND; ++id) digest_slab_call<LA, LB, LC, LD, NK>(I, jab, pab, a, fa, fb, fc, fd, kacc, ic, id);
+            for (int id = 0; id < ND; ++id) digest_slab_call<LA, LB, LC, LD, NK>(I, jab, pab, a, fx, fa, fb, fc, fd, kacc, ic, id);
     } else {
 #pragma unroll
         for (int ic = 0; ic < NC; ++ic)
 #pragma unroll
-            for (int id = 0; id < ND; ++id) digest_slab_impl<LA, LB, LC, LD, NK>(I, jab, pab, a, fa, fb, fc, fd, kacc, ic, id);
+            for (int id = 0; id < ND; ++id) digest_slab_impl<LA, LB, LC, LD, NK>(I, jab, pab, a, fx, fa, fb, fc, fd, kacc, ic, id);
     }
 }
 
-// ---- the block Fock-build kernel: one CTA per (bra pair, chunk of its ket prefix); s/p/ds bras -------
-// NK = number of exchange densities (1: RHF / single-density J,K;  2: UHF alpha,beta).
-template <int LA, int LB, int LC, int LD, int NK>
-__global__ void __launch_bounds__(128)
-eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
-    using KA = KAcc<LA, LB, LC, LD>;
-    constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
-    constexpr int NAB = NA * NB, NCD = NC * ND, NI = NAB * NCD;
-    const int ib_ = a.rank + blockIdx.x * a.world;
-    if (ib_ >= bra.npair) return;
-    const double qab = __ldg(bra.Q + ib_);
-    // ket prefix that survives Q_ab Q_cd Dmax >= tau (ket Q sorted descending)
+// ---- ket scan shared by the two Fock-build kernels -----------------------------------------------------
+// One scan step: every lane tests SW candidate kets (scan + j*32 + lane), all loads issued up front (coalesced:
+// Q, the pair's own density maximum Dp, the two shell ids), then the density-weighted screening
+//     Q_ab Q_cd max(D_ab, D_cd, max(D_ac, D_ad, D_bc, D_bd)/2) >= tau,
+// and the survivors are appended to the warp's queue in list order.  Returns the new queue length.
+// The scan is latency-bound (two dependent memory round trips per step), so its throughput is the number of
+// candidates in flight: SW = 4 keeps 128 per warp instead of 32.
+template <int SW>
+__device__ __forceinline__ int scan_kets(const PairGroup& ket, const double tau, const int scan, const int nket, const double qab,
+                                         const float dab, const float* __restrict__ dsh_a, const float* __restrict__ dsh_b,
+                                         int* __restrict__ queue, int qn, const int lane) {
+    bool ok[SW];
+    if (tau > 0.0) {
+        double qcd[SW];
+        float dcd[SW];
+        int sc[SW], sd[SW];
+#pragma unroll
+        for (int j = 0; j < SW; ++j) {
+            const int ikc = scan + j * 32 + lane;
+            ok[j] = ikc < nket;
+            const int ii = ok[j] ? ikc : scan;          // scan < nket: always a valid index
+            qcd[j] = __ldg(ket.Q + ii); dcd[j] = __ldg(ket.Dp + ii);
+            sc[j] = __ldg(ket.sa + ii); sd[j] = __ldg(ket.sb + ii);
+        }
+#pragma unroll
+        for (int j = 0; j < SW; ++j) {
+            float dm = fmaxf(dab, dcd[j]);
+            const float dk = fmaxf(fmaxf(dsh_a[sc[j]], dsh_a[sd[j]]), fmaxf(dsh_b[sc[j]], dsh_b[sd[j]]));
+            dm = fmaxf(dm, 0.5f * dk);
+            ok[j] = ok[j] && !(qab * qcd[j] * (double)dm < tau);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SW; ++j) ok[j] = scan + j * 32 + lane < nket;
+    }
+#pragma unroll
+    for (int j = 0; j < SW; ++j) {
+        const unsigned int m = __ballot_sync(0xffffffffu, ok[j]);
+        if (ok[j]) queue[qn + __popc(m & ((1u << lane) - 1u))] = scan + j * 32 + lane;
+        qn += __popc(m);
+    }
+    return qn;
+}
+
+// ket prefix of bra pair ib_ that can survive Q_ab Q_cd Dmax >= tau (ket list sorted by descending Q bucket),
+// clipped to this CTA's chunk [ket0, ket0 + chunk); returns the end index (<= ket0: nothing to do)
+__device__ __forceinline__ int ket_prefix_end(const PairGroup& ket, const BuildArgs& a, double qab, int ib_, int same_group, int ket0) {
     int nket = ket.npair;
     if (a.tau > 0.0) {
-        const double need = a.tau / (qab * a.dmax);
+        const double dmax = fmax((double)__uint_as_float(a.sc->dmax_bits), 1e-300);
+        const double need = a.tau / (qab * dmax);
         int lo = 0, hi = ket.npair;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(ket.Qb + mid) >= need) lo = mid + 1; else hi = mid; }
         nket = lo;
     }
     if (same_group && nket > ib_ + 1) nket = ib_ + 1;
-    const int ket0 = blockIdx.y * a.ket_chunk;
-    if (nket <= ket0) return;
     if (nket > ket0 + a.ket_chunk) nket = ket0 + a.ket_chunk;
+    return nket;
+}
+
+// ---- the block Fock-build kernel: one CTA per (bra pair, chunk of its ket prefix); s/p/ds bras -------
+// NK = number of exchange densities (1: RHF / single-density J,K;  2: UHF alpha,beta).
+// PS = lanes per shell quartet (1, or 4 / 8 for the highly contracted launches, see contracted_quartet_staged).
+#ifndef QCF_SCANW
+#define QCF_SCANW 4
+#endif
+template <int PS> struct BlockCfg {
+    static constexpr int SW = PS == 1 ? QCF_SCANW : 1;        // scan width: a PS > 1 warp consumes only 32/PS quartets per pass
+    static constexpr int QLEN = 32 * (SW + 1);
+};
+template <int LA, int LB, int LC, int LD, int NK, int PS>
+__global__ void __launch_bounds__(128)
+eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
+    using KA = KAcc<LA, LB, LC, LD>;
+    constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
+    constexpr int NAB = NA * NB, NCD = NC * ND, NI = NAB * NCD;
+    constexpr int SW = BlockCfg<PS>::SW, QLEN = BlockCfg<PS>::QLEN, QPW = 32 / PS;
+    const int ib_ = a.bra_list ? __ldg(a.bra_list + blockIdx.x) : (int)blockIdx.x;
+    const double qab = __ldg(bra.Q + ib_);
+    const int ket0 = blockIdx.y * a.ket_chunk;
+    const int nket = ket_prefix_end(ket, a, qab, ib_, same_group, ket0);
+    if (nket <= ket0) return;
+    const double fx = a.sc->fx_scale;
 
     const int N = a.N;
     const int fa = __ldg(bra.fa + ib_), fb = __ldg(bra.fb + ib_);
     const int sa = __ldg(bra.sa + ib_), sb = __ldg(bra.sb + ib_);
     const double bra_deg = (sa == sb) ? 0.5 : 1.0;
-    const float dab = __ldg(a.Dsh + (size_t)sa * a.nshell + sb);
+    const float dab = __ldg(bra.Dp + ib_);
 
     // CTA-constant data in shared memory: the bra primitives and the two rows (shell a, shell b) of the
     // shell-block density maxima that the exchange screening gathers from
@@ -604,49 +710,42 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     for (int i = 0; i < NAB; ++i) { jab[i] = 0.0; pab[i] = __ldg(a.Pj + (size_t)(fa + i / NB) * N + fb + i % NB); }
     unsigned int nq = 0;
 
-    // Warp-level compaction of the surviving kets: every warp scans 32 candidate kets at a time, applies the
+    // Warp-level compaction of the surviving kets: every warp scans 32*SW candidate kets at a time, applies the
     // density-weighted screening, and queues the survivors in shared memory; the expensive part below always
-    // runs on (up to) 32 survivors, one per lane, so screened-out kets cost a scan step instead of an idle
-    // lane for a whole contracted quartet (lane utilisation was 21-25 of 32 without it).
-    __shared__ int ket_queue[4][64];
+    // runs on (up to) 32/PS survivors, PS lanes each, so screened-out kets cost a scan step instead of an idle
+    // lane for a whole contracted quartet.
+    __shared__ int ket_queue[4][QLEN];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = lane / PS, sub = lane % PS;
+    int* const queue = ket_queue[warp];
     int qn = 0;
-    int scan = ket0 + warp * 32;
+    int scan = ket0 + warp * (32 * SW);
+    const int scan_stride = (int)blockDim.x * SW;
     while (true) {
-        while (qn < 32 && scan < nket) {
-            const int ikc = scan + lane;
-            bool ok = ikc < nket;
-            if (ok && a.tau > 0.0) {
-                const double qcd = __ldg(ket.Q + ikc);
-                const int sc = __ldg(ket.sa + ikc), sd = __ldg(ket.sb + ikc);
-                float dm = fmaxf(dab, __ldg(a.Dsh + (size_t)sc * a.nshell + sd));
-                float dk = fmaxf(fmaxf(dsh_a[sc], dsh_a[sd]), fmaxf(dsh_b[sc], dsh_b[sd]));
-                dm = fmaxf(dm, 0.5f * dk);
-                ok = !(qab * qcd * (double)dm < a.tau);
-            }
-            const unsigned int m = __ballot_sync(0xffffffffu, ok);
-            if (ok) ket_queue[warp][qn + __popc(m & ((1u << lane) - 1u))] = ikc;
-            qn += __popc(m);
-            scan += blockDim.x;
+        while (qn < QPW && scan < nket) {
+            qn = scan_kets<SW>(ket, a.tau, scan, nket, qab, dab, dsh_a, dsh_b, queue, qn, lane);
+            scan += scan_stride;
         }
         __syncwarp();
-        const int nrun = qn < 32 ? qn : 32;
+        const int nrun = qn < QPW ? qn : QPW;
         if (nrun == 0) break;
-        if (lane < nrun) {
-        const int ik_ = ket_queue[warp][qn - nrun + lane];
+        const unsigned int amask = __ballot_sync(0xffffffffu, slot < nrun);
+        if (slot < nrun) {
+        const int ik_ = queue[qn - nrun + slot];
         const int sc = __ldg(ket.sa + ik_), sd = __ldg(ket.sb + ik_);
-        ++nq;
+        if (sub == 0) ++nq;
         const int fc = __ldg(ket.fa + ik_), fd = __ldg(ket.fb + ik_);
         double deg = bra_deg * ((sc == sd) ? 0.5 : 1.0);
         if (same_group && ik_ == ib_) deg *= 0.5;
 
         double I[NI];
-        contracted_quartet_staged<LA, LB, LC, LD>(bra_s, nkb, ABx, ABy, ABz, ket, ik_, deg, a.boys, I);
+        contracted_quartet_staged<LA, LB, LC, LD, PS>(bra_s, nkb, ABx, ABy, ABz, ket, ik_, deg, a.boys, sub, amask, I);
 
+        if (sub == 0) {
         double kacc[NK * KA::SIZE];
 #pragma unroll
         for (int i = 0; i < NK * KA::SIZE; ++i) kacc[i] = 0.0;
-        digest_all<LA, LB, LC, LD, NK>(I, jab, pab, a, fa, fb, fc, fd, kacc);
+        digest_all<LA, LB, LC, LD, NK>(I, jab, pab, a, fx, fa, fb, fc, fd, kacc);
 #pragma unroll
         for (int kk = 0; kk < NK; ++kk) {
             double* __restrict__ AK = kk == 0 ? a.AK0 : a.AK1;
@@ -654,24 +753,25 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
 #pragma unroll
             for (int i = 0; i < NA; ++i) {
 #pragma unroll
-                for (int j = 0; j < NC; ++j) red_add(AK + (size_t)(fa + i) * N + fc + j, acc[KA::OFF_AC + i * NC + j]);
+                for (int j = 0; j < NC; ++j) red_add(AK + (size_t)(fa + i) * N + fc + j, acc[KA::OFF_AC + i * NC + j], fx);
 #pragma unroll
-                for (int j = 0; j < ND; ++j) red_add(AK + (size_t)(fa + i) * N + fd + j, acc[KA::OFF_AD + i * ND + j]);
+                for (int j = 0; j < ND; ++j) red_add(AK + (size_t)(fa + i) * N + fd + j, acc[KA::OFF_AD + i * ND + j], fx);
             }
 #pragma unroll
             for (int i = 0; i < NB; ++i) {
 #pragma unroll
-                for (int j = 0; j < NC; ++j) red_add(AK + (size_t)(fb + i) * N + fc + j, acc[KA::OFF_BC + i * NC + j]);
+                for (int j = 0; j < NC; ++j) red_add(AK + (size_t)(fb + i) * N + fc + j, acc[KA::OFF_BC + i * NC + j], fx);
 #pragma unroll
-                for (int j = 0; j < ND; ++j) red_add(AK + (size_t)(fb + i) * N + fd + j, acc[KA::OFF_BD + i * ND + j]);
+                for (int j = 0; j < ND; ++j) red_add(AK + (size_t)(fb + i) * N + fd + j, acc[KA::OFF_BD + i * ND + j], fx);
             }
         }
-        }   // lane < nrun
+        }   // sub == 0
+        }   // slot < nrun
         qn -= nrun;
         __syncwarp();
     }
 
-    // ---- J_ab: reduce over the CTA, one atomic per element ----
+    // ---- J_ab: reduce over the CTA (fixed order), one atomic per element ----
     __shared__ double red[4][NAB];
 #pragma unroll
     for (int i = 0; i < NAB; ++i) {
@@ -686,7 +786,7 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     for (int i = threadIdx.x; i < NAB; i += blockDim.x) {
         double s = 0.0;
         for (int w = 0; w < nwarp; ++w) s += red[w][i];
-        red_add(a.AJ + (size_t)(fa + i / NB) * N + fb + i % NB, s);
+        red_add(a.AJ + (size_t)(fa + i / NB) * N + fb + i % NB, s, fx);
     }
     if (threadIdx.x == 0) {
         unsigned int t = 0;
@@ -723,7 +823,11 @@ __global__ void quartet_kernel(PairGroup bra, int ib_, PairGroup ket, int ik_, c
 
 // ---- launch interface of one angular class (defined in eri_class.cu, one object per class) ------
 struct ClassLaunch {
-    void (*jk)(int nk, int nbra, int nket_max, int block, int kets_per_thread, cudaStream_t s, const PairGroup& bra, const PairGroup& ket, const BuildArgs& a, int same);
+    // ps = lanes per shell quartet (1, 4 or 8; block kernel only)
+    void (*jk)(int nk, int ps, int nbra, int nket_max, int block, int kets_per_thread, cudaStream_t s, const PairGroup& bra, const PairGroup& ket, const BuildArgs& a, int same);
+    // one-off per device: opt in to the dynamic shared memory the largest launch of this class needs
+    cudaError_t (*init)(int max_bra_K, int nshell);
+    int max_ps;           // largest ps this class was compiled for
     void (*quartet)(cudaStream_t s, const PairGroup& bra, int ib_, const PairGroup& ket, int ik_, const double* boys, double* out);
     void (*schwarz)(int grid, int block, cudaStream_t s, const PairGroup& g, const double* boys, double* Q);  // null unless (LA,LB)==(LC,LD)
 };

@@ -145,7 +145,7 @@ template <int LA, int LB, int LC, int LD, int NK, int SPT, int IA, int... IB>
 __device__ __forceinline__ void digest_a(std::integer_sequence<int, IB...>, const int SG, const double (&Hs)[SPT][nherm(LA + LB)],
                                          const double* __restrict__ e3, const double* __restrict__ pab_s,
                                          double* __restrict__ jab_s, double (&jab)[ncart(LA) * ncart(LB)],
-                                         DigestState<NK, SPT, ncart(LB)>& d, const BuildArgs& a, int fa, int fc, int fd) {
+                                         DigestState<NK, SPT, ncart(LB)>& d, const BuildArgs& a, const double fx, int fa, int fc, int fd) {
     constexpr int ND = ncart(LD);
     const int N = a.N;
 #pragma unroll
@@ -166,8 +166,8 @@ __device__ __forceinline__ void digest_a(std::integer_sequence<int, IB...>, cons
 #pragma unroll
         for (int kk = 0; kk < NK; ++kk) {
             double* __restrict__ AK = kk == 0 ? a.AK0 : a.AK1;
-            red_add(AK + (size_t)(fa + IA) * N + fc + IC, d.kac[kk][s]);
-            red_add(AK + (size_t)(fa + IA) * N + fd + ID, d.kad[kk][s]);
+            red_add(AK + (size_t)(fa + IA) * N + fc + IC, d.kac[kk][s], fx);
+            red_add(AK + (size_t)(fa + IA) * N + fd + ID, d.kad[kk][s], fx);
         }
     }
 }
@@ -176,8 +176,8 @@ template <int LA, int LB, int LC, int LD, int NK, int SPT, int... IA>
 __device__ __forceinline__ void digest_all_a(std::integer_sequence<int, IA...>, const int SG, const double (&Hs)[SPT][nherm(LA + LB)],
                                              const double* __restrict__ e3, const double* __restrict__ pab_s,
                                              double* __restrict__ jab_s, double (&jab)[ncart(LA) * ncart(LB)],
-                                             DigestState<NK, SPT, ncart(LB)>& d, const BuildArgs& a, int fa, int fc, int fd) {
-    (digest_a<LA, LB, LC, LD, NK, SPT, IA>(std::make_integer_sequence<int, ncart(LB)>{}, SG, Hs, e3, pab_s, jab_s, jab, d, a, fa, fc, fd), ...);
+                                             DigestState<NK, SPT, ncart(LB)>& d, const BuildArgs& a, const double fx, int fa, int fc, int fd) {
+    (digest_a<LA, LB, LC, LD, NK, SPT, IA>(std::make_integer_sequence<int, ncart(LB)>{}, SG, Hs, e3, pab_s, jab_s, jab, d, a, fx, fa, fc, fd), ...);
 }
 
 // The slab group enters only through the ket component offsets (IC, ID) of the global addresses, so it is a
@@ -185,7 +185,7 @@ __device__ __forceinline__ void digest_all_a(std::integer_sequence<int, IA...>, 
 template <int LA, int LB, int LC, int LD, int NK, int SPT>
 __device__ __forceinline__ void slab_digest(const int SG, const double (&Hs)[SPT][nherm(LA + LB)], const double* __restrict__ e3,
                                             const double* __restrict__ pab_s, double* __restrict__ jab_s,
-                                            double (&jab)[ncart(LA) * ncart(LB)], const BuildArgs& a, int fa, int fb, int fc, int fd) {
+                                            double (&jab)[ncart(LA) * ncart(LB)], const BuildArgs& a, const double fx, int fa, int fb, int fc, int fd) {
     using C = SlabCfg<LA, LB, LC, LD, NK, SPT>;
     constexpr int NA = C::NA, NB = C::NB, ND = C::ND;
     const int N = a.N;
@@ -206,18 +206,18 @@ __device__ __forceinline__ void slab_digest(const int SG, const double (&Hs)[SPT
             }
         }
     }
-    digest_all_a<LA, LB, LC, LD, NK, SPT>(std::make_integer_sequence<int, NA>{}, SG, Hs, e3, pab_s, jab_s, jab, d, a, fa, fc, fd);
+    digest_all_a<LA, LB, LC, LD, NK, SPT>(std::make_integer_sequence<int, NA>{}, SG, Hs, e3, pab_s, jab_s, jab, d, a, fx, fa, fc, fd);
 #pragma unroll
     for (int s = 0; s < SPT; ++s) {
         const int icd = SG * SPT + s, IC = icd / ND, ID = icd % ND;
-        red_add(a.AJ + (size_t)(fc + IC) * N + fd + ID, d.scd[s]);
+        red_add(a.AJ + (size_t)(fc + IC) * N + fd + ID, d.scd[s], fx);
 #pragma unroll
         for (int kk = 0; kk < NK; ++kk) {
             double* __restrict__ AK = kk == 0 ? a.AK0 : a.AK1;
 #pragma unroll
             for (int i = 0; i < NB; ++i) {
-                red_add(AK + (size_t)(fb + i) * N + fc + IC, d.kbc[kk][s][i]);
-                red_add(AK + (size_t)(fb + i) * N + fd + ID, d.kbd[kk][s][i]);
+                red_add(AK + (size_t)(fb + i) * N + fc + IC, d.kbc[kk][s][i], fx);
+                red_add(AK + (size_t)(fb + i) * N + fd + ID, d.kbd[kk][s][i], fx);
             }
         }
     }
@@ -248,26 +248,18 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     constexpr int NA = C::NA, NB = C::NB, NAB = C::NAB, L = C::L, NH = C::NH, G = C::G, NSUB = C::NSUB, BLOCK = C::BLOCK;
     extern __shared__ __align__(16) double smem[];
     __shared__ int off_s[NAB];
-    const int ib_ = a.rank + blockIdx.x * a.world;
-    if (ib_ >= bra.npair) return;
+    const int ib_ = a.bra_list ? __ldg(a.bra_list + blockIdx.x) : (int)blockIdx.x;
     const double qab = __ldg(bra.Q + ib_);
-    int nket = ket.npair;
-    if (a.tau > 0.0) {
-        const double need = a.tau / (qab * a.dmax);
-        int lo = 0, hi = ket.npair;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(ket.Qb + mid) >= need) lo = mid + 1; else hi = mid; }
-        nket = lo;
-    }
-    if (same_group && nket > ib_ + 1) nket = ib_ + 1;
     const int ket0 = blockIdx.y * a.ket_chunk;
+    const int nket = ket_prefix_end(ket, a, qab, ib_, same_group, ket0);
     if (nket <= ket0) return;
-    if (nket > ket0 + a.ket_chunk) nket = ket0 + a.ket_chunk;
+    const double fx = a.sc->fx_scale;
 
     const int N = a.N, KAB = __ldg(bra.nprim + ib_);
     const int fa = __ldg(bra.fa + ib_), fb = __ldg(bra.fb + ib_);
     const int sa = __ldg(bra.sa + ib_), sb = __ldg(bra.sb + ib_);
     const double bra_deg = (sa == sb) ? 0.5 : 1.0;
-    const float dab = __ldg(a.Dsh + (size_t)sa * a.nshell + sb);
+    const float dab = __ldg(bra.Dp + ib_);
 
     // ---- shared-memory tables of the bra pair -------------------------------------------------------
     double* const tab = smem;                                  // [KAB][STRIDE]
@@ -338,26 +330,17 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
 
     // warp-level compaction of the surviving kets (see eri_jk_kernel): scan 32 candidates, queue the survivors,
     // run the quartet work on full warps
-    __shared__ int ket_queue[NSUB][64];
+    constexpr int SW = 2;
+    __shared__ int ket_queue[NSUB][32 * (SW + 1)];
+    const float* const dsh_a = a.Dsh + (size_t)sa * a.nshell;     // rows of the shell-block maxima (global, L1-resident)
+    const float* const dsh_b = a.Dsh + (size_t)sb * a.nshell;
+    int* const queue = ket_queue[ksub];
     int qn = 0;
-    int scan = ket0 + ksub * 32;
+    int scan = ket0 + ksub * (32 * SW);
     while (true) {
         while (qn < 32 && scan < nket) {
-            const int ikc = scan + lane;
-            bool ok = ikc < nket;
-            if (ok && a.tau > 0.0) {
-                const double qcd = __ldg(ket.Q + ikc);
-                const int sc = __ldg(ket.sa + ikc), sd = __ldg(ket.sb + ikc);
-                float dm = fmaxf(dab, __ldg(a.Dsh + (size_t)sc * a.nshell + sd));
-                float dk = fmaxf(fmaxf(__ldg(a.Dsh + (size_t)sa * a.nshell + sc), __ldg(a.Dsh + (size_t)sa * a.nshell + sd)),
-                                 fmaxf(__ldg(a.Dsh + (size_t)sb * a.nshell + sc), __ldg(a.Dsh + (size_t)sb * a.nshell + sd)));
-                dm = fmaxf(dm, 0.5f * dk);
-                ok = !(qab * qcd * (double)dm < a.tau);
-            }
-            const unsigned int m = __ballot_sync(0xffffffffu, ok);
-            if (ok) ket_queue[ksub][qn + __popc(m & ((1u << lane) - 1u))] = ikc;
-            qn += __popc(m);
-            scan += 32 * NSUB;
+            qn = scan_kets<SW>(ket, a.tau, scan, nket, qab, dab, dsh_a, dsh_b, queue, qn, lane);
+            scan += 32 * NSUB * SW;
         }
         __syncwarp();
         const int nrun = qn < 32 ? qn : 32;
@@ -401,7 +384,7 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
                 hermite_R<L, false>(c, X, Y, Z, R);
                 dispatch_ket<LA, LB, LC, LD, NK, SPT, 0>(sg, R, Ecd, Hs);
             }
-            slab_digest<LA, LB, LC, LD, NK, SPT>(sg, Hs, tb + EL::E3_OFF, pab_s, jab_s, jab, a, fa, fb, fc, fd);
+            slab_digest<LA, LB, LC, LD, NK, SPT>(sg, Hs, tb + EL::E3_OFF, pab_s, jab_s, jab, a, fx, fa, fb, fc, fd);
         }
         }   // lane < nrun
         qn -= nrun;
@@ -415,7 +398,7 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
             double s = 0.0;
             for (int t = lane; t < BLOCK; t += 32) s += jab_all[i * BLOCK + t];
             s = warp_sum(s);
-            if (lane == 0) red_add(a.AJ + (size_t)(fa + i / NB) * N + fb + i % NB, s);
+            if (lane == 0) red_add(a.AJ + (size_t)(fa + i / NB) * N + fb + i % NB, s, fx);
         }
     } else {
         double* red = smem;    // tables are dead now: [BLOCK/32][NAB]
@@ -428,7 +411,7 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
         for (int i = threadIdx.x; i < NAB; i += BLOCK) {
             double s = 0.0;
             for (int w = 0; w < BLOCK / 32; ++w) s += red[w * NAB + i];
-            red_add(a.AJ + (size_t)(fa + i / NB) * N + fb + i % NB, s);
+            red_add(a.AJ + (size_t)(fa + i / NB) * N + fb + i % NB, s, fx);
         }
     }
     nq = __reduce_add_sync(0xffffffffu, nq);

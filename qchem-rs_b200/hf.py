@@ -186,3 +186,71 @@ def unrestricted_hartree_fock(system, config: HartreeFockConfig, integrals, fock
                                                  nuclear_repulsion, iteration, dens[0], dens[1],
                                                  f_keep[0], f_keep[1])
     return None
+
+
+class IncrementalFock:
+    """Fock builder for the host SCF loops above that uses the engine's difference-density builds:
+    G_k = G_{k-1} + G(P_k - P_{k-1}), a full rebuild every `full_every` iterations."""
+
+    def __init__(self, engine, full_every: int = 8):
+        self.eng = engine
+        self.full_every = max(1, int(full_every))
+        self.n = 0
+        self.log = []      # (iteration, quartets, kernel_ms) per build
+
+    def _reset(self):
+        r = (self.n % self.full_every) == 0
+        self.n += 1
+        return r
+
+    def rhf(self, P):
+        g = self.eng.rhf_incremental(P, reset=self._reset())
+        st = self.eng.stats()
+        self.log.append((self.n - 1, st["quartets"], st["kernel_ms"]))
+        return g
+
+    def uhf(self, Pa, Pb):
+        g = self.eng.uhf_incremental(Pa, Pb, reset=self._reset())
+        st = self.eng.stats()
+        self.log.append((self.n - 1, st["quartets"], st["kernel_ms"]))
+        return g
+
+
+def restricted_hartree_fock_device(system, config: HartreeFockConfig, integrals, engine,
+                                   full_rebuild_every: int = 0) -> Optional[RestrictedHartreeFockOutput]:
+    """rhf.rs:32-108 with the whole iteration on the GPU (qcf_scf_init / qcf_scf_step):
+    P, G, F, the DIIS history and the orbitals stay in HBM; the host sees scalars only."""
+    S, T, V = integrals
+    engine.scf_init(S, T + V, system.n_electrons() // 2, unrestricted=False, full_rebuild_every=full_rebuild_every)
+    nuclear_repulsion = compute_nuclear_repulsion(system.atoms)
+    steps = []
+    for _ in range(config.max_iterations + 1):
+        info = engine.scf_step(config.epsilon)
+        steps.append(info)
+        if info["converged"]:
+            out = RestrictedHartreeFockOutput(engine.scf_get("orbital_energies"), info["electronic_energy"], nuclear_repulsion,
+                                              info["iteration"], engine.scf_get("density"), engine.scf_get("fock"),
+                                              [s["build_ms"] * 1e-3 for s in steps])
+            out.steps = steps
+            return out
+    return None
+
+
+def unrestricted_hartree_fock_device(system, config: HartreeFockConfig, integrals, engine, n_alpha: Optional[int] = None,
+                                     n_beta: Optional[int] = None, full_rebuild_every: int = 0
+                                     ) -> Optional[UnrestrictedHartreeFockOutput]:
+    """uhf.rs:36-189 on the GPU.  n_alpha / n_beta default to the reference semantics (n_electrons / 2 each)."""
+    S, T, V = integrals
+    n_el = system.n_electrons()
+    n_alpha = n_el // 2 if n_alpha is None else n_alpha
+    n_beta = n_el // 2 if n_beta is None else n_beta
+    engine.scf_init(S, T + V, n_alpha, n_beta, unrestricted=True, full_rebuild_every=full_rebuild_every)
+    nuclear_repulsion = compute_nuclear_repulsion(system.atoms)
+    for _ in range(config.max_iterations + 1):
+        info = engine.scf_step(config.epsilon)
+        if info["converged"]:
+            return UnrestrictedHartreeFockOutput(engine.scf_get("orbital_energies", 0), engine.scf_get("orbital_energies", 1),
+                                                 info["electronic_energy"], nuclear_repulsion, info["iteration"],
+                                                 engine.scf_get("density", 0), engine.scf_get("density", 1),
+                                                 engine.scf_get("fock", 0), engine.scf_get("fock", 1))
+    return None

@@ -75,3 +75,97 @@ def test_ctypes_mirrors_match_the_header_layout(tmp_path):
     assert sizes == [ctypes.sizeof(CBasis), ctypes.sizeof(engine.COpts), ctypes.sizeof(engine.CStats), ctypes.sizeof(engine.CLaunchRec)]
     assert offs == [CBasis.cartesian.offset, engine.COpts.block_threads.offset, engine.CStats.prim_pairs_kept.offset,
                     engine.CLaunchRec.ms.offset]
+
+
+def test_scf_info_layout_matches_header(tmp_path):
+    import subprocess
+    from qchem_rs_b200 import engine
+    src = tmp_path / "layout2.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "qcfock.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu\\n", sizeof(qcf_scf_info), offsetof(qcf_scf_info, wall_ms),\n'
+                   '  offsetof(qcf_opts, deterministic), offsetof(qcf_stats_t, rank_imbalance)); return 0; }\n')
+    exe = tmp_path / "layout2"
+    subprocess.check_call(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)])
+    out = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    assert out == [ctypes.sizeof(engine.CScfInfo), engine.CScfInfo.wall_ms.offset, engine.COpts.deterministic.offset,
+                   engine.CStats.rank_imbalance.offset]
+
+
+def _flat_water():
+    from helpers import load_system
+    return load_system("water", "STO-3G").flat()
+
+
+def test_create_rejects_bad_basis_arrays_before_touching_the_gpu():
+    """Argument validation of qcf_create: more than 255 primitives in a shell (the primitive-pair index is
+    16 bit), negative primitive offsets, non-positive exponents and l > 2 are QCF_ERR_ARG with a message."""
+    import numpy as np
+    from qchem_rs_b200 import engine
+    L = engine.lib()
+
+    def create(fb):
+        ctx = ctypes.c_void_p()
+        rc = L.qcf_create(fb.ref(), None, ctypes.byref(ctx))
+        msg = L.qcf_last_error(ctx).decode() if ctx else ""
+        if ctx:
+            L.qcf_destroy(ctx)
+        return rc, msg
+
+    fb = _flat_water()
+    fb.shell_nprim[0] = 300
+    rc, msg = create(fb)
+    assert rc == -1 and "255" in msg
+    fb = _flat_water()
+    fb.shell_prim_off[1] = -3
+    rc, msg = create(fb)
+    assert rc == -1 and "shell_prim_off" in msg
+    fb = _flat_water()
+    fb.exps[2] = -1.0
+    rc, msg = create(fb)
+    assert rc == -1 and "exponent" in msg
+    fb = _flat_water()
+    fb.shell_l[0] = 3
+    rc, msg = create(fb)
+    assert rc == -1 and "angular" in msg
+    fb = _flat_water()
+    fb.c.cartesian = 0
+    rc, msg = create(fb)
+    assert rc == -1 and "Cartesian" in msg
+
+
+@pytest.mark.parametrize("mol,basis", [("water", "STO-3G"), ("benzene", "6-31G"), ("caffeine", "6-31G_st"), ("hydrogen", "STO-3G"),
+                                       ("oxygen", "6-31G"), ("ethylene", "6-31G")])
+def test_native_loaders_match_python_loaders(mol, basis):
+    """qcf_system_load (C++ JSON loaders behind the C ABI, stand-in for BasisSet::load / MolecularSystem::load,
+    main.rs:76-77) on the reference's own data files against the Python loaders the other tests use."""
+    import numpy as np
+    from helpers import load_system, DATA
+    from qchem_rs_b200 import engine, hf
+    system = load_system(mol, basis)
+    fb = system.flat()
+    nat = engine.NativeSystem(DATA / "basis" / f"{basis}.json", DATA / "mol" / f"{mol}.json")
+    assert nat.n_basis == fb.n_basis and nat.n_electrons == system.n_electrons()
+    np.testing.assert_array_equal(nat.Z, fb.Z)
+    np.testing.assert_array_equal(nat.shell_l, fb.shell_l)
+    np.testing.assert_array_equal(nat.shell_atom, fb.shell_atom)
+    np.testing.assert_array_equal(nat.shell_nprim, fb.shell_nprim)
+    np.testing.assert_array_equal(nat.shell_prim_off, fb.shell_prim_off)
+    np.testing.assert_array_equal(nat.xyz, fb.xyz)
+    np.testing.assert_array_equal(nat.exps, fb.exps)
+    np.testing.assert_allclose(nat.coefs, fb.coefs, rtol=1e-15)
+    assert nat.nuclear_repulsion == pytest.approx(hf.compute_nuclear_repulsion(system.atoms), rel=1e-15)
+
+
+def test_native_loader_errors_are_reported(tmp_path):
+    from helpers import DATA
+    from qchem_rs_b200 import engine
+    with pytest.raises(engine.FockError, match="cannot open"):
+        engine.NativeSystem(tmp_path / "missing.json", DATA / "mol" / "water.json")
+    bad = tmp_path / "bad.json"
+    bad.write_text('[{"element": "8", "position": [0, 0]}]')
+    with pytest.raises(engine.FockError, match="malformed atom"):
+        engine.NativeSystem(DATA / "basis" / "STO-3G.json", bad)
+    heavy = tmp_path / "u.json"
+    heavy.write_text('[{"element": "92", "position": [0, 0, 0]}]')
+    with pytest.raises(engine.FockError, match="no element"):
+        engine.NativeSystem(DATA / "basis" / "STO-3G.json", heavy)

@@ -1,0 +1,346 @@
+"""GPU parity tests added in round 2 (run with -m gpu on a B200): parity at the benchmarked sizes against an
+UNSCREENED oracle, exact symmetry, the deterministic mode, incremental builds, the device-resident SCF step and the
+in-library multi-GPU path.  Everything goes through the C ABI of libqcfock.so.
+
+Tolerances (north_star): max |dF_ij| < 1e-9 (unscaled), |dE_total| < 1e-8 Eh, same SCF iteration count."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import load_system, water_cluster, random_symmetric_density, oracle_lib
+from qchem_rs_b200 import hf, engine
+
+pytestmark = pytest.mark.gpu
+
+F_TOL = 1e-9
+E_TOL = 1e-8
+
+
+def scf_density(system, ints, builder, iters):
+    """Density that enters the Fock build of SCF iteration `iters` of the reference's RHF loop (0 = Hueckel guess)."""
+    seen = {}
+
+    class Tap:
+        def rhf(self, P):
+            seen["P"] = np.array(P, copy=True)
+            return builder.rhf(P)
+    hf.restricted_hartree_fock(system, hf.HartreeFockConfig(iters, 1e-14), ints, Tap())
+    return seen["P"]
+
+
+def sample_shell_pairs(fb, G, n_random, seed):
+    """Shell pairs whose G blocks are checked: every (l_a, l_b) type, diagonal blocks, the blocks holding the largest
+    |G| elements, and a random sample."""
+    ns = len(fb.shell_l)
+    off = np.concatenate([[0], np.cumsum([(l + 1) * (l + 2) // 2 for l in fb.shell_l])])
+    rng = np.random.default_rng(seed)
+    pairs = set()
+    by_type = {}
+    for _ in range(20000):
+        a, b = (int(x) for x in rng.integers(0, ns, size=2))
+        by_type.setdefault((int(fb.shell_l[a]), int(fb.shell_l[b])), (a, b))
+        if len(by_type) == 9:
+            break
+    pairs.update(by_type.values())
+    for s in rng.integers(0, ns, size=4):
+        pairs.add((int(s), int(s)))
+    fun2shell = np.repeat(np.arange(ns), np.diff(off))
+    flat = np.argsort(np.abs(G), axis=None)[::-1][:200]
+    for f in flat[::25]:
+        i, j = np.unravel_index(f, G.shape)
+        pairs.add((int(fun2shell[i]), int(fun2shell[j])))
+    while len(pairs) < len(by_type) + 12 + n_random:
+        a, b = (int(x) for x in rng.integers(0, ns, size=2))
+        pairs.add((a, b))
+    return sorted(pairs), off
+
+
+@pytest.mark.parametrize("nwater,nblocks", [(27, 40), (53, 40)])
+def test_fock_parity_at_benchmark_size_against_unscreened_oracle(nwater, nblocks):
+    """(H2O)_27 (N = 513) and (H2O)_53 (N = 1007, the benchmarked configuration) / 6-31G*: G, J and K of the GPU build
+    at tau = 1e-12 on the SCF-iteration-6 density against the oracle's EXACT contraction -- no Schwarz, density, pair
+    or primitive screening of any kind (oracle_lib.jk_blocks_exact restates rhf.rs:58-62 + 152-167 for one shell
+    block) -- on ~60 sampled shell-pair blocks, max |dG| < 1e-9 UNSCALED.  The N^4 tensor of the reference would need
+    554 GB / 8 TB here, a full unscreened direct build 7e8 / 1e10 quartets; a block needs ~n_shell^2."""
+    system = water_cluster(nwater)
+    fb = system.flat()
+    n = fb.n_basis
+    assert n == 19 * nwater
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        ints = eng.one_electron()
+        P = scf_density(system, ints, eng, 6)
+        G = eng.rhf(P)
+        st = eng.stats()
+        (J,), (K,) = eng.jk([P])
+    assert np.array_equal(G, G.T), "G must be exactly symmetric (utils.rs:7-13)"
+    assert np.array_equal(J, J.T) and np.array_equal(K, K.T)
+    assert 0 < st["prim_pairs_kept"] <= st["prim_pairs"]
+    assert 0 < st["quartets"] < st["quartets_total"]
+    pairs, off = sample_shell_pairs(fb, G, nblocks, seed=100 + nwater)
+    Jb, Kb = oracle_lib.jk_blocks_exact(fb, P, pairs)
+    worst = {"G": 0.0, "J": 0.0, "K": 0.0}
+    for (a, b), jb, kb in zip(pairs, Jb, Kb):
+        sl = (slice(off[a], off[a + 1]), slice(off[b], off[b + 1]))
+        worst["J"] = max(worst["J"], float(np.max(np.abs(J[sl] - jb))))
+        worst["K"] = max(worst["K"], float(np.max(np.abs(K[sl] - kb))))
+        worst["G"] = max(worst["G"], float(np.max(np.abs(G[sl] - (jb - 0.5 * kb)))))
+    print(f"(H2O)_{nwater} N={n}: {len(pairs)} blocks, max|dG|={worst['G']:.2e} max|dJ|={worst['J']:.2e} max|dK|={worst['K']:.2e}; "
+          f"prim pairs kept {st['prim_pairs_kept']}/{st['prim_pairs']}, quartets {st['quartets']}/{st['quartets_total']}")
+    assert worst["G"] < F_TOL and worst["J"] < F_TOL and worst["K"] < F_TOL
+
+
+def test_uhf_parity_at_513_basis_functions_against_unscreened_oracle():
+    """alpha/beta digestion at size: (H2O)_27, unequal random-perturbed densities, G_a = J[Pa+Pb] - K[Pa] (uhf.rs:210-227)."""
+    system = water_cluster(27)
+    fb = system.flat()
+    n = fb.n_basis
+    rng = np.random.default_rng(7)
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        ints = eng.one_electron()
+        P = scf_density(system, ints, eng, 3)
+        d = rng.normal(size=(n, n)) * 1e-2
+        Pa = 0.5 * P + 0.5 * (d + d.T)
+        Pb = 0.5 * P - 0.25 * (d + d.T)
+        Ga, Gb = eng.uhf(Pa, Pb)
+    assert np.array_equal(Ga, Ga.T) and np.array_equal(Gb, Gb.T)
+    pairs, off = sample_shell_pairs(fb, Ga, 10, seed=5)
+    pairs = pairs[:24]
+    Ja, Ka = oracle_lib.jk_blocks_exact(fb, Pa, pairs)
+    Jb, Kb = oracle_lib.jk_blocks_exact(fb, Pb, pairs)
+    for i, (a, b) in enumerate(pairs):
+        sl = (slice(off[a], off[a + 1]), slice(off[b], off[b + 1]))
+        assert np.max(np.abs(Ga[sl] - (Ja[i] + Jb[i] - Ka[i]))) < F_TOL
+        assert np.max(np.abs(Gb[sl] - (Ja[i] + Jb[i] - Kb[i]))) < F_TOL
+
+
+def test_caffeine_converged_density_strict_parity():
+    """BASELINE config 4, strict: caffeine / 6-31G* RHF converged on the GPU, then G(P_converged) against the oracle's
+    direct build with NO screening (tau = 0), max |dG| < 1e-9 unscaled, and the energy expression on both."""
+    system = load_system("caffeine", "6-31G_st")
+    fb = system.flat()
+    assert fb.n_basis == 230
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        ints = eng.one_electron()
+        out = hf.restricted_hartree_fock(system, hf.HartreeFockConfig(100, 1e-7), ints, eng)
+        assert out is not None and out.iterations < 60
+        P = out.density
+        G = eng.rhf(P)
+    assert np.array_equal(G, G.T)
+    ref = oracle_lib.DirectFock(fb, tau=0.0).rhf(P)
+    assert np.max(np.abs(G - ref)) < F_TOL
+    h = ints[1] + ints[2]
+    assert abs(0.5 * np.trace(P @ (2 * h + G)) - 0.5 * np.trace(P @ (2 * h + ref))) < E_TOL
+    assert -680.0 < out.total_energy() < -670.0
+
+
+def test_quartet_count_close_to_oracle_at_equal_tau():
+    """Same screening rule on both sides: the GPU evaluates a superset (power-of-two Schwarz buckets for the prefix
+    cut, float density maxima rounded up), never fewer quartets than the oracle needs, and at most a few per cent more
+    -- minus the pairs dropped at creation (Q < 1e-2 tau / Q_max), which the oracle also skips through the rule."""
+    system = water_cluster(5)
+    fb = system.flat()
+    with engine.FockEngine(system, tau=1e-10) as eng:
+        ints = eng.one_electron()
+        P = scf_density(system, ints, eng, 4)
+        G = eng.rhf(P)
+        q_gpu = eng.stats()["quartets"]
+    d = oracle_lib.DirectFock(fb, tau=1e-10)
+    ref = d.rhf(P)
+    assert np.max(np.abs(G - ref)) < 1e-8        # two screened builds at a loose tau
+    assert d.last_quartets <= q_gpu <= 1.05 * d.last_quartets
+
+
+def test_deterministic_mode_is_bitwise_reproducible():
+    """qcf_opts.deterministic: fixed-point accumulation with 64-bit integer atomics.  Two builds of the same density
+    -- and a second context -- give bit-identical matrices; the result agrees with the FP64-atomic path and with the
+    dense oracle."""
+    system = water_cluster(3)
+    fb = system.flat()
+    n = fb.n_basis
+    P = random_symmetric_density(n, 21)
+    Pa, Pb = random_symmetric_density(n, 22), random_symmetric_density(n, 23)
+    with engine.FockEngine(system, tau=1e-12, deterministic=True) as eng:
+        g1 = eng.rhf(P)
+        g2 = eng.rhf(P)
+        a1, b1 = eng.uhf(Pa, Pb)
+        a2, b2 = eng.uhf(Pa, Pb)
+    with engine.FockEngine(system, tau=1e-12, deterministic=True) as eng:
+        g3 = eng.rhf(P)
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        g0 = eng.rhf(P)
+    assert np.array_equal(g1, g2) and np.array_equal(g1, g3)
+    assert np.array_equal(a1, a2) and np.array_equal(b1, b2)
+    assert np.array_equal(g1, g1.T)
+    assert np.max(np.abs(g1 - g0)) < 1e-10
+    assert np.max(np.abs(g1 - oracle_lib.DenseFock(fb).rhf(P))) < F_TOL
+
+
+def test_deterministic_scf_runs_are_identical_benzene_reference_geometry():
+    """The reference's own data/mol/benzene.json follows a chaotic early trajectory (see test_gpu_parity): with the
+    deterministic mode two free-running GPU SCF runs are bit-identical -- iteration count, energy, Fock matrix --
+    which settles that the +-1 iteration slack of the non-deterministic path comes from atomic ordering."""
+    system = load_system("benzene", "6-31G")
+    runs = []
+    for _ in range(2):
+        with engine.FockEngine(system, tau=1e-12, deterministic=True) as eng:
+            ints = eng.one_electron()
+            runs.append(hf.restricted_hartree_fock(system, hf.HartreeFockConfig(100, 1e-8), ints, eng))
+    assert runs[0] is not None and runs[1] is not None
+    assert runs[0].iterations == runs[1].iterations
+    assert runs[0].electronic_energy == runs[1].electronic_energy
+    assert np.array_equal(runs[0].fock, runs[1].fock)
+
+
+def test_graph_replay_equals_stream_launches():
+    """The build is replayed as one CUDA graph per device; QCF_NO_GRAPH=1 launches the same kernels on streams."""
+    system = water_cluster(2)
+    n = system.n_basis()
+    P = random_symmetric_density(n, 31)
+    with engine.FockEngine(system, tau=1e-12, deterministic=True) as eng:
+        g_graph = eng.rhf(P)
+        st = eng.stats()
+        g_again = eng.rhf(P)
+    assert st["graph_launches"] == 1 and st["launches"] > 10
+    os.environ["QCF_NO_GRAPH"] = "1"
+    try:
+        with engine.FockEngine(system, tau=1e-12, deterministic=True) as eng:
+            g_stream = eng.rhf(P)
+            assert eng.stats()["graph_launches"] == 0
+    finally:
+        del os.environ["QCF_NO_GRAPH"]
+    assert np.array_equal(g_graph, g_again) and np.array_equal(g_graph, g_stream)
+
+
+def test_incremental_builds_match_full_builds_along_an_scf():
+    """qcf_build_rhf_incremental: G_k = G_{k-1} + G(P_k - P_{k-1}) with difference-density screening, full rebuild every
+    6 iterations.  Same iteration count and energy as the full-build run, every G within 1e-9 of the full build, and the
+    late builds evaluate far fewer quartets."""
+    system = water_cluster(6)
+    fb = system.flat()
+    cfg = hf.HartreeFockConfig(100, 1e-8)
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        ints = eng.one_electron()
+        full = hf.restricted_hartree_fock(system, cfg, ints, eng, keep_history=True)
+        q_full = eng.stats()["quartets"]
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        inc = hf.IncrementalFock(eng, full_every=6)
+        got = hf.restricted_hartree_fock(system, cfg, ints, inc, keep_history=True)
+    assert full is not None and got is not None
+    assert got.iterations == full.iterations
+    assert abs(got.total_energy() - full.total_energy()) < E_TOL
+    for (_, _, _, f1), (_, _, _, f2) in zip(full.history, got.history):
+        assert np.max(np.abs(f1 - f2)) < F_TOL
+    late = [q for (it, q, _) in inc.log if it % 6 != 0 and it >= full.iterations - 3]
+    assert late and min(late) < 0.9 * q_full
+    # UHF flavour: one incremental step equals the full build
+    n = fb.n_basis
+    Pa, Pb = random_symmetric_density(n, 1), random_symmetric_density(n, 2)
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        ga, gb = eng.uhf(Pa, Pb)
+        eng.uhf_incremental(0.9 * Pa, 1.1 * Pb, reset=True)
+        ia, ib = eng.uhf_incremental(Pa, Pb)
+    assert np.max(np.abs(ia - ga)) < F_TOL and np.max(np.abs(ib - gb)) < F_TOL
+
+
+@pytest.mark.parametrize("name", ["water_sto3g", "benzene_d6h_631g", "water2_631gs"])
+def test_device_resident_rhf_matches_host_loop(name):
+    """qcf_scf_init / qcf_scf_step (cuBLAS + cuSOLVER on the device, P and G never leave HBM) against the host loop
+    of hf.py (numpy) driving the same engine: iteration count, energy, density, Fock matrix, orbital energies."""
+    if name == "water_sto3g":
+        system = load_system("water", "STO-3G")
+    elif name == "benzene_d6h_631g":
+        system = load_system("benzene_d6h", "6-31G")
+    else:
+        system = water_cluster(2)
+    cfg = hf.HartreeFockConfig(100, 1e-8)
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        ints = eng.one_electron()
+        host = hf.restricted_hartree_fock(system, cfg, ints, eng)
+        dev = hf.restricted_hartree_fock_device(system, cfg, ints, eng)
+        dev_inc = hf.restricted_hartree_fock_device(system, cfg, ints, eng, full_rebuild_every=5)
+    assert host is not None and dev is not None and dev_inc is not None
+    for out in (dev, dev_inc):
+        assert out.iterations == host.iterations
+        assert abs(out.total_energy() - host.total_energy()) < E_TOL
+        assert np.max(np.abs(out.fock - host.fock)) < 1e-7
+        assert np.max(np.abs(out.density - host.density)) < 1e-6
+        np.testing.assert_allclose(out.orbital_energies, host.orbital_energies, atol=1e-7)
+
+
+def test_device_resident_uhf_matches_host_loop():
+    """UHF step on the device with unequal occupations (labelled extension n_alpha = 5, n_beta = 4 electrons of a water
+    cation-like occupation on the neutral geometry): compare with the host loop for a fixed number of iterations."""
+    system = load_system("water", "3-21G")
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        ints = eng.one_electron()
+        S, T, V = ints
+        eng.scf_init(S, T + V, 5, 4, unrestricted=True)
+        infos = [eng.scf_step(1e-9) for _ in range(8)]
+        pa, pb = eng.scf_get("density", 0), eng.scf_get("density", 1)
+        # host loop, same number of iterations
+        seen = {}
+
+        class Tap:
+            def uhf(self, A, B):
+                seen["n"] = seen.get("n", 0) + 1
+                return eng.uhf(A, B)
+        hf.unrestricted_hartree_fock(system, hf.HartreeFockConfig(7, 1e-30), ints, Tap(), n_alpha=5, n_beta=4)
+    assert seen["n"] == 8
+    assert all(np.isfinite(i["electronic_energy"]) for i in infos)
+    assert abs(np.trace(pa @ S) - 5.0) < 1e-9 and abs(np.trace(pb @ S) - 4.0) < 1e-9
+    assert infos[-1]["density_rms"] < infos[0]["density_rms"]
+
+
+def test_in_library_multi_gpu_matches_single_gpu():
+    """qcf_opts.n_gpus: one context drives several GPUs from one host thread -- cost-balanced bra split,
+    density replicated by peer copies, partial accumulators summed over NVLink peer memory inside the finalize kernel.
+    Needs >= 2 visible GPUs (skipped on a single-GPU box; the rank split itself is covered by
+    test_bra_partition_sums_to_full_build)."""
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs at least 2 GPUs")
+    system = water_cluster(4)
+    n = system.n_basis()
+    P = random_symmetric_density(n, 41)
+    Pa, Pb = random_symmetric_density(n, 42), random_symmetric_density(n, 43)
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        g1 = eng.rhf(P)
+        a1, b1 = eng.uhf(Pa, Pb)
+        q1 = eng.stats()["quartets"]
+    for k in sorted({2, min(ng, 4), ng}):
+        with engine.FockEngine(system, tau=1e-12, n_gpus=k) as eng:
+            gk = eng.rhf(P)
+            st = eng.stats()
+            ak, bk = eng.uhf(Pa, Pb)
+            times = eng.device_times()
+        assert st["n_devices"] == k and len(times) == k and st["quartets"] == q1
+        assert np.max(np.abs(gk - g1)) < 1e-11 and np.array_equal(gk, gk.T)
+        assert np.max(np.abs(ak - a1)) < 1e-11 and np.max(np.abs(bk - b1)) < 1e-11
+    with engine.FockEngine(system, tau=1e-12, n_gpus=2, deterministic=True) as eng:
+        d1 = eng.rhf(P)
+        d2 = eng.rhf(P)
+    assert np.array_equal(d1, d2) and np.max(np.abs(d1 - g1)) < 1e-10
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_cost_balanced_split_covers_every_bra_once(world):
+    """The cost-modelled split (one global load vector over all groups): partial builds of all ranks sum to the
+    single-rank matrix and the quartet counts add up; the modelled imbalance is small."""
+    system = water_cluster(4)
+    n = system.n_basis()
+    P = random_symmetric_density(n, 51)
+    with engine.FockEngine(system, tau=1e-12) as eng:
+        full = eng.rhf(P)
+        q_full = eng.stats()["quartets"]
+    acc = np.zeros_like(full)
+    q = 0
+    for r in range(world):
+        with engine.FockEngine(system, tau=1e-12, rank=r, world_size=world) as eng:
+            acc += eng.rhf(P)
+            st = eng.stats()
+            q += st["quartets"]
+            assert 1.0 <= st["rank_imbalance"] < 1.02
+    np.testing.assert_allclose(acc, full, atol=1e-11)
+    assert q == q_full
