@@ -27,6 +27,8 @@ struct HostGroup {
 struct GroupDev {
     int *fa = nullptr, *fb = nullptr, *sa = nullptr, *sb = nullptr, *np = nullptr;
     double *Q = nullptr, *Qb = nullptr, *prim = nullptr, *AB = nullptr;
+    int4* meta = nullptr;               // {fa, fb, sa | sb << 16, nprim} per pair
+    int* ssp = nullptr;                 // sa | sb << 16 per pair
     int* bra_list = nullptr;            // this device's share of the group's bra pairs (null: all of them)
     int nbra = 0;
     qcf::PairGroup pg{};

@@ -188,11 +188,8 @@ int diis_fock(qcf_ctx* ctx, qcf_scf* s, Diis& d, const double* err, const double
     CK(cudaMemcpyAsync(slot.fock, fock, nn * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
     d.samples.push_front(slot);
     const int n = (int)d.samples.size();
-    if (n < d.min_len) {
-        CK(cudaMemcpyAsync(out, fock, nn * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
-        return QCF_OK;
-    }
-    // new dot products <e_0, e_j>; older ones are cached
+    // dot products <e_0, e_j> of the newest error matrix with every kept one (older pairs are cached); computed on every
+    // call, also while n < min_len, because those samples enter the B matrix later
     CKB(cublasSetPointerMode(s->blas, CUBLAS_POINTER_MODE_DEVICE));
     for (int j = 0; j < n; ++j)
         CKB(cublasDdot(s->blas, (int)nn, d.samples[0].err, 1, d.samples[j].err, 1, s->scal + j));
@@ -203,6 +200,10 @@ int diis_fock(qcf_ctx* ctx, qcf_scf* s, Diis& d, const double* err, const double
     for (int j = 0; j < n; ++j) {
         d.dots[{d.samples[0].id, d.samples[j].id}] = hd[j];
         d.dots[{d.samples[j].id, d.samples[0].id}] = hd[j];
+    }
+    if (n < d.min_len) {
+        CK(cudaMemcpyAsync(out, fock, nn * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        return QCF_OK;
     }
     const int m = n + 1;
     std::vector<double> B((size_t)m * m, 0.0), rhs(m, 0.0), c;
