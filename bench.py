@@ -334,6 +334,8 @@ def run_b200(args):
     # ---- e2e: the drop-in C-ABI call with HOST buffers ------------------------------------------------------------
     st0 = eng.stats()
     e2e = None
+    multi_check = None
+    g_nccl = fock.rhf(P) if world > 1 else None       # all ranks take part in the all-reduce
     if world == 1:
         ms_e, q_e, _, _, _ = timed(lambda: eng.rhf(P), args.steps, max(1, args.warmup // 2), eng)
         e2e = {"value": q_e / (ms_e * 1e-3), "ms_per_step": ms_e / args.steps, "path": "qcf_build_rhf, one context, one GPU"}
@@ -346,6 +348,13 @@ def run_b200(args):
                 ms_e, q_e, _, _, _ = timed(lambda: eng_all.rhf(P), args.steps, max(2, args.warmup // 2), eng_all, sync=False)
                 dev_ms = eng_all.device_times()
                 st_all = eng_all.stats()
+                g_all = eng_all.rhf(P)
+            # the N-GPU results against a plain single-GPU build of the same density (outside every timed region)
+            with pkg.engine.FockEngine(system, tau=args.tau, device=0) as eng_one:
+                g_one = eng_one.rhf(P)
+            multi_check = {"max_abs_diff_nccl_ranks_vs_1gpu": float(np.max(np.abs(g_nccl - g_one))),
+                           "max_abs_diff_inlibrary_ngpu_vs_1gpu": float(np.max(np.abs(g_all - g_one))),
+                           "symmetric": bool(np.array_equal(g_all, g_all.T) and np.array_equal(g_nccl, g_nccl.T))}
             e2e = {"value": q_e / (ms_e * 1e-3), "ms_per_step": ms_e / args.steps,
                    "path": f"qcf_build_rhf, ONE context with n_gpus={world} in rank 0's process (single host thread)",
                    "device_ms": dev_ms, "host_enqueue_ms": st_all["host_ms"], "create_ms": st_all["create_ms"],
@@ -408,6 +417,8 @@ def run_b200(args):
         if e2e is not None:
             e2e.update({"unit": UNIT, "h2d_bytes_per_step": 8 * n * n, "d2h_bytes_per_step": 8 * n * n})
             line["e2e"] = e2e
+        if multi_check is not None:
+            line["config"]["multi_gpu_check"] = multi_check
         if scf is not None:
             line["config"]["scf"] = scf
         if cpu is not None:

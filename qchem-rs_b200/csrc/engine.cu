@@ -263,8 +263,7 @@ __global__ void fp64_peak_kernel(double* out, int iters, double x) {
 
 // ---- pair construction -------------------------------------------------------------------------------
 struct PairArrays {
-    std::vector<int> fa, fb, sa, sb, np, ssp;
-    std::vector<int4> meta;
+    std::vector<int> fa, fb, sa, sb, np;
     std::vector<double> Q, Qb, prim, AB;
 };
 
@@ -275,9 +274,8 @@ inline double q_bucket_ceiling(double Q) { return Q > 0 ? std::ldexp(1.0, q_buck
 void fill_pair_arrays(const qcf_ctx* c, const HostGroup& g, PairArrays& out) {
     const size_t np = g.pairs.size();
     out.fa.resize(np); out.fb.resize(np); out.sa.resize(np); out.sb.resize(np); out.Q.resize(np); out.Qb.resize(np); out.np.resize(np);
-    out.ssp.resize(np); out.meta.resize(np);
     out.prim.assign((size_t)g.K * PF_COUNT * np, 0.0);
-    out.AB.assign(4 * np, 0.0);
+    out.AB.assign(3 * np, 0.0);
     const double cpi = std::sqrt(2.0) * std::pow(PI_D, 1.25);
     for (size_t i = 0; i < np; ++i) {
         const int sa = g.pairs[i].sa, sb = g.pairs[i].sb;
@@ -285,10 +283,8 @@ void fill_pair_arrays(const qcf_ctx* c, const HostGroup& g, PairArrays& out) {
         const double* A = &c->xyz[3 * c->sh_atom[sa]];
         const double* B = &c->xyz[3 * c->sh_atom[sb]];
         double AB2 = 0;
-        for (int k = 0; k < 3; ++k) { out.AB[4 * i + k] = A[k] - B[k]; AB2 += (A[k] - B[k]) * (A[k] - B[k]); }
+        for (int k = 0; k < 3; ++k) { out.AB[k * np + i] = A[k] - B[k]; AB2 += (A[k] - B[k]) * (A[k] - B[k]); }
         out.np[i] = g.pairs[i].keff < 0 ? g.K : g.pairs[i].keff;
-        out.ssp[i] = sa | (sb << 16);
-        out.meta[i] = make_int4(out.fa[i], out.fb[i], out.ssp[i], out.np[i]);
         const int npb = c->sh_np[sb];
         for (int kk = 0; kk < g.K; ++kk) {
             const int ksel = g.pairs[i].order.empty() ? kk : g.pairs[i].order[kk];
@@ -296,14 +292,14 @@ void fill_pair_arrays(const qcf_ctx* c, const HostGroup& g, PairArrays& out) {
             const double a = c->exps[c->sh_po[sa] + ia], b = c->exps[c->sh_po[sb] + ib];
             const double ca = c->coefs[c->sh_po[sa] + ia], cb = c->coefs[c->sh_po[sb] + ib];
             const double p = a + b, mu = a * b / p;
-            double* f = &out.prim[((size_t)kk * np + i) * PF_COUNT];
-            f[PF_P] = p;
+            double* f = &out.prim[(size_t)kk * PF_COUNT * np + i];
+            f[PF_P * np] = p;
             for (int k = 0; k < 3; ++k) {
                 const double Pk = (a * A[k] + b * B[k]) / p;
-                f[PF_PX + k] = Pk;
-                f[PF_PAX + k] = Pk - A[k];
+                f[(PF_PX + k) * np] = Pk;
+                f[(PF_PAX + k) * np] = Pk - A[k];
             }
-            f[PF_C] = cpi * ca * cb * std::exp(-mu * AB2) / p;
+            f[PF_C * np] = cpi * ca * cb * std::exp(-mu * AB2) / p;
         }
     }
 }
@@ -318,7 +314,7 @@ cudaError_t upload(T** dptr, const std::vector<T>& h) {
 
 void free_group(GroupDev& g) {
     cudaFree(g.fa); cudaFree(g.fb); cudaFree(g.sa); cudaFree(g.sb); cudaFree(g.np); cudaFree(g.Q); cudaFree(g.Qb); cudaFree(g.prim); cudaFree(g.AB);
-    cudaFree(g.bra_list); cudaFree(g.meta); cudaFree(g.ssp);
+    cudaFree(g.bra_list);
     g = GroupDev{};
 }
 
@@ -329,10 +325,8 @@ int upload_group(qcf_ctx* ctx, const HostGroup& g, GroupDev& d) {
     free_group(d);
     CK(upload(&d.fa, pa.fa)); CK(upload(&d.fb, pa.fb)); CK(upload(&d.sa, pa.sa)); CK(upload(&d.sb, pa.sb)); CK(upload(&d.np, pa.np));
     CK(upload(&d.Q, pa.Q)); CK(upload(&d.Qb, pa.Qb)); CK(upload(&d.prim, pa.prim)); CK(upload(&d.AB, pa.AB));
-    CK(upload(&d.meta, pa.meta)); CK(upload(&d.ssp, pa.ssp));
     d.pg.npair = (int)g.pairs.size(); d.pg.K = g.K; d.pg.la = g.la; d.pg.lb = g.lb;
     d.pg.fa = d.fa; d.pg.fb = d.fb; d.pg.sa = d.sa; d.pg.sb = d.sb; d.pg.nprim = d.np; d.pg.Q = d.Q; d.pg.Qb = d.Qb; d.pg.prim = d.prim; d.pg.AB = d.AB;
-    d.pg.meta = d.meta; d.pg.ssp = d.ssp;
     d.pg.Dp = nullptr;
     d.nbra = d.pg.npair;
     return QCF_OK;
@@ -481,9 +475,12 @@ void make_plan(qcf_ctx* ctx) {
             const double nq = (double)bra.pairs.size() * ket.pairs.size() * (gi == gj ? 0.5 : 1.0);
             ctx->plan.push_back({gi, gj, 0, ps, pq / ps, nq * pq});
         }
-    std::stable_sort(ctx->plan.begin(), ctx->plan.end(), [](const PlannedLaunch& x, const PlannedLaunch& y) {
-        return x.serial != y.serial ? x.serial > y.serial : x.cost > y.cost;
-    });
+    if (ctx->launch_order == 1)         // biggest launches first
+        std::stable_sort(ctx->plan.begin(), ctx->plan.end(), [](const PlannedLaunch& x, const PlannedLaunch& y) { return x.cost > y.cost; });
+    else                                // default: longest-running threads first, then biggest
+        std::stable_sort(ctx->plan.begin(), ctx->plan.end(), [](const PlannedLaunch& x, const PlannedLaunch& y) {
+            return x.serial != y.serial ? x.serial > y.serial : x.cost > y.cost;
+        });
     // Cost-balanced static split of every group's bra list over the ranks: modelled cost of bra pair i =
     // sum over the ket groups it is paired with of (length of its Schwarz prefix at a nominal density maximum of 1) x
     // (primitive quartets x op count of the class); heaviest first onto the least loaded rank, one global load
@@ -943,6 +940,8 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     if (const char* e = getenv("QCF_SERIAL_CAP")) ctx->serial_cap = std::max(1.0, atof(e));
     if (const char* e = getenv("QCF_TARGET_CTAS")) ctx->target_ctas = std::max(1, atoi(e));
     if (const char* e = getenv("QCF_PS_MIN")) ctx->ps_min_prim = std::max(1, atoi(e));
+    if (const char* e = getenv("QCF_BLOCK")) ctx->block = atoi(e);
+    if (const char* e = getenv("QCF_ORDER")) ctx->launch_order = atoi(e);
     if (ctx->block < 32 || ctx->block > 128 || ctx->block % 32) return fail(QCF_ERR_ARG, "block_threads must be 32, 64, 96 or 128");
     ctx->natoms = b->n_atoms; ctx->nshell = b->n_shells;
     ctx->xyz.assign(b->xyz, b->xyz + 3 * b->n_atoms);
@@ -961,7 +960,6 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
         if (ctx->sh_np[s] > 255) return fail(QCF_ERR_ARG, "more than 255 primitives in one shell");
         if (ctx->sh_po[s] < 0) return fail(QCF_ERR_ARG, "negative shell_prim_off");
         if (ctx->sh_atom[s] < 0 || ctx->sh_atom[s] >= b->n_atoms) return fail(QCF_ERR_ARG, "shell_atom out of range");
-        if (b->n_shells > 32767) return fail(QCF_ERR_ARG, "more than 32767 shells (shell ids are packed into 16 bits)");
         nprim = std::max(nprim, (long long)ctx->sh_po[s] + ctx->sh_np[s]);
         ctx->sh_off[s + 1] = ctx->sh_off[s] + ncart(ctx->sh_l[s]);
     }

@@ -27,8 +27,6 @@ struct HostGroup {
 struct GroupDev {
     int *fa = nullptr, *fb = nullptr, *sa = nullptr, *sb = nullptr, *np = nullptr;
     double *Q = nullptr, *Qb = nullptr, *prim = nullptr, *AB = nullptr;
-    int4* meta = nullptr;               // {fa, fb, sa | sb << 16, nprim} per pair
-    int* ssp = nullptr;                 // sa | sb << 16 per pair
     int* bra_list = nullptr;            // this device's share of the group's bra pairs (null: all of them)
     int nbra = 0;
     qcf::PairGroup pg{};
@@ -78,6 +76,7 @@ struct qcf_ctx {
     double serial_cap = 4e6;          // model flops one thread may run serially in one launch
     double tau = 1e-12;
     bool screening = true, deterministic = false, use_graph = true, profile = false;
+    int launch_order = 0;             // 0: longest-running threads first; 1: biggest launches first (QCF_ORDER)
     int ps_min_prim = 36;             // primitive quartets per shell quartet from which lanes share a quartet
     int world = 1;                    // total number of ranks in the bra split (processes x devices)
     // basis (host copies)

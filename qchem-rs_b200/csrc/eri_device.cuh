@@ -38,9 +38,9 @@ __host__ __device__ constexpr int hidx(int t, int u, int v) {
 // One "pair group" = all significant shell pairs of one (la >= lb) class with the same number of
 // primitive pairs K, sorted by power-of-two Schwarz bucket (descending) and, inside a bucket, by shell
 // indices, so that neighbouring lanes gather/scatter neighbouring density and Fock elements.
-// Primitive data: one 64-byte record per (primitive k, pair i) at prim[(k * npair + i) * PF_COUNT], fields in PrimField
-// order, read with two 256-bit loads (LDG.E.256); consecutive kets (= consecutive lanes) read consecutive records.
-// Per-pair integers travel as one int4 (`meta`), the pair geometry A - B as one 32-byte record.
+// Structure of arrays: field f of primitive k of pair i sits at prim[(k * PF_COUNT + f) * npair + i], so consecutive kets (= consecutive lanes)
+// read consecutive doubles.  (Round 2 measured the alternatives on the N = 1007 build: 64-byte records per primitive read
+// with 256-bit loads -- neutral for the block kernel, 20-40 % slower for the slab kernel; see profiles/README.md.)
 enum PrimField { PF_P = 0, PF_PX, PF_PY, PF_PZ, PF_C, PF_PAX, PF_PAY, PF_PAZ, PF_COUNT };
 struct PairGroup {
     int npair, K, la, lb;
@@ -51,10 +51,8 @@ struct PairGroup {
     const int* nprim;     // primitive pairs kept for this pair (<= K; sorted by primitive Schwarz factor, negligible ones dropped)
     const double* Q;      // Schwarz factor
     const double* Qb;     // power-of-two bucket ceiling of Q, non-increasing along the list (prefix search)
-    const double* prim;   // [K][npair][PF_COUNT];  PF_C = sqrt(2) pi^(5/4) c_a c_b exp(-mu AB^2) / p
-    const double* AB;     // [npair][4]  A - B (x, y, z, pad)
-    const int4* meta;     // [npair]  {fa, fb, sa | sb << 16, nprim}
-    const int* ssp;       // [npair]  sa | sb << 16 (the ket scan reads this array alone)
+    const double* prim;   // [K][PF_COUNT][npair];  PF_C = sqrt(2) pi^(5/4) c_a c_b exp(-mu AB^2) / p
+    const double* AB;     // [3][npair]  A - B
     const float* Dp;      // [npair] max |P| over the pair's shell block, rewritten by every build (pair_dmax_kernel)
 };
 
@@ -102,15 +100,6 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return r * r;
 }
 
-// ---- 256-bit read-only global load (LDG.E.256 on sm_100a; the address must be 32-byte aligned) ----------
-struct D4 { double x, y, z, w; };
-__device__ __forceinline__ D4 ldg256(const double* p) {
-    D4 v;
-    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int4 ldg_meta(const int4* p) { return __ldg(p); }
-
 // ---- Boys function -----------------------------------------------------------------------------
 // F_0..F_L(T).  T < boys_tmax(L) (36 .. 64): 7-term Taylor expansion of F_L about the nearest grid point (table row holds
 // F_{L+k}(T0)/k!), then the stable downward recursion F_{m-1} = (2T F_m + e^-T)/(2m-1).  Above:
@@ -125,10 +114,9 @@ __device__ __forceinline__ void boys(double T, const double* __restrict__ table,
         const int g = (int)(T * BOYS_PER_UNIT + 0.5);
         const double d = (double)g * (1.0 / BOYS_PER_UNIT) - T;
         const double* r = table + ((size_t)L * BOYS_NGRID + g) * BOYS_ROW;
-        const D4 lo = ldg256(r), hi = ldg256(r + 4);      // the whole 64-byte row in two loads
-        double f = hi.z;
-        f = fma(f, d, hi.y); f = fma(f, d, hi.x); f = fma(f, d, lo.w);
-        f = fma(f, d, lo.z); f = fma(f, d, lo.y); f = fma(f, d, lo.x);
+        double f = __ldg(r + 6);
+#pragma unroll
+        for (int k = 5; k >= 0; --k) f = fma(f, d, __ldg(r + k));
         F[L] = f;
         if constexpr (L > 0) {
             // exp(-T) = exp(-T0) exp(d), |d| <= 1/32: row slot 7 holds exp(-T0); 8-term Taylor (< 1e-19)
@@ -136,7 +124,7 @@ __device__ __forceinline__ void boys(double T, const double* __restrict__ table,
             ed = fma(ed, d, 1.0 / 5040.0); ed = fma(ed, d, 1.0 / 720.0); ed = fma(ed, d, 1.0 / 120.0);
             ed = fma(ed, d, 1.0 / 24.0); ed = fma(ed, d, 1.0 / 6.0); ed = fma(ed, d, 0.5);
             ed = fma(ed, d, 1.0); ed = fma(ed, d, 1.0);
-            const double e = hi.w * ed;
+            const double e = __ldg(r + 7) * ed;
             const double t2 = 2.0 * T;
 #pragma unroll
             for (int m = L; m > 0; --m) F[m - 1] = fma(t2, F[m], e) * (1.0 / (2 * m - 1));
@@ -368,28 +356,23 @@ template <int LA, int LB>
 __device__ __forceinline__ void load_prim(const PairGroup& g, int i, int k, double ABx, double ABy, double ABz,
                                           double& p, double& Px, double& Py, double& Pz, double& cP,
                                           PairE<LA, LB>& E, bool ket_sign) {
-    const double* base = g.prim + ((size_t)k * g.npair + i) * PF_COUNT;
-    const D4 lo = ldg256(base);
-    p = lo.x; Px = lo.y; Py = lo.z; Pz = lo.w;
+    const double* base = g.prim + (size_t)k * PF_COUNT * g.npair + i;
+    const size_t np = g.npair;
+    p = __ldg(base + PF_P * np);
+    Px = __ldg(base + PF_PX * np);
+    Py = __ldg(base + PF_PY * np);
+    Pz = __ldg(base + PF_PZ * np);
+    cP = __ldg(base + PF_C * np);
     if constexpr (LA + LB > 0) {
-        const D4 hi = ldg256(base + 4);
-        cP = hi.x;
         const double h = 0.5 * fast_rcp(p);
-        const double pax = hi.y, pay = hi.z, paz = hi.w;
+        const double pax = __ldg(base + PF_PAX * np), pay = __ldg(base + PF_PAY * np), paz = __ldg(base + PF_PAZ * np);
         // P - B = (P - A) + (A - B)
         E.ax[0].build(h, pax, pax + ABx, ket_sign);
         E.ax[1].build(h, pay, pay + ABy, ket_sign);
         E.ax[2].build(h, paz, paz + ABz, ket_sign);
     } else {
-        cP = __ldg(base + PF_C);
         E.ax[0].e[0] = 1.0; E.ax[1].e[0] = 1.0; E.ax[2].e[0] = 1.0;
     }
-}
-
-// A - B of pair i
-__device__ __forceinline__ void load_AB(const PairGroup& g, int i, double& x, double& y, double& z) {
-    const D4 v = ldg256(g.AB + 4 * (size_t)i);
-    x = v.x; y = v.y; z = v.z;
 }
 
 // contracted quartet block of (bra pair ib_, ket pair ik_), scaled by `scale`
@@ -401,8 +384,12 @@ __device__ __forceinline__ void contracted_quartet(const PairGroup& bra, int ib_
 #pragma unroll
     for (int i = 0; i < NI; ++i) I[i] = 0.0;
     double ABx = 0, ABy = 0, ABz = 0, CDx = 0, CDy = 0, CDz = 0;
-    if constexpr (LB > 0) load_AB(bra, ib_, ABx, ABy, ABz);
-    if constexpr (LD > 0) load_AB(ket, ik_, CDx, CDy, CDz);
+    if constexpr (LB > 0) {
+        ABx = __ldg(bra.AB + ib_); ABy = __ldg(bra.AB + bra.npair + ib_); ABz = __ldg(bra.AB + 2 * (size_t)bra.npair + ib_);
+    }
+    if constexpr (LD > 0) {
+        CDx = __ldg(ket.AB + ik_); CDy = __ldg(ket.AB + ket.npair + ik_); CDz = __ldg(ket.AB + 2 * (size_t)ket.npair + ik_);
+    }
     const int nkc = __ldg(ket.nprim + ik_), nkb = __ldg(bra.nprim + ib_);
     for (int kc = 0; kc < nkc; ++kc) {
         double q, Qx, Qy, Qz, cQ;
@@ -425,8 +412,8 @@ constexpr int BRA_S = 9;    // doubles per staged bra primitive: PrimField order
 __device__ __forceinline__ void stage_bra(const PairGroup& g, int ib_, int nkb, double* __restrict__ dst) {
     for (int t = threadIdx.x; t < nkb * BRA_S; t += blockDim.x) {
         const int kb = t / BRA_S, f = t % BRA_S;
-        const double* base = g.prim + ((size_t)kb * g.npair + ib_) * PF_COUNT;
-        dst[t] = f < PF_COUNT ? __ldg(base + f) : 0.5 / __ldg(base + PF_P);
+        const double* base = g.prim + (size_t)kb * PF_COUNT * g.npair + ib_;
+        dst[t] = f < PF_COUNT ? __ldg(base + (size_t)f * g.npair) : 0.5 / __ldg(base + (size_t)PF_P * g.npair);
     }
 }
 template <int LA, int LB>
@@ -450,14 +437,17 @@ __device__ __forceinline__ void load_prim_staged(const double* __restrict__ b, d
 // one thread while few such quartets exist -- a latency tail).
 template <int LA, int LB, int LC, int LD, int PS>
 __device__ __forceinline__ void contracted_quartet_staged(const double* __restrict__ bra_s, int nkb, double ABx, double ABy, double ABz,
-                                                          const PairGroup& ket, int ik_, const int nkc, double scale,
+                                                          const PairGroup& ket, int ik_, double scale,
                                                           const double* __restrict__ boys_table, int sub, unsigned int amask,
                                                           double (&I)[ncart(LA) * ncart(LB) * ncart(LC) * ncart(LD)]) {
     constexpr int NI = ncart(LA) * ncart(LB) * ncart(LC) * ncart(LD);
 #pragma unroll
     for (int i = 0; i < NI; ++i) I[i] = 0.0;
     double CDx = 0, CDy = 0, CDz = 0;
-    if constexpr (LD > 0) load_AB(ket, ik_, CDx, CDy, CDz);
+    if constexpr (LD > 0) {
+        CDx = __ldg(ket.AB + ik_); CDy = __ldg(ket.AB + ket.npair + ik_); CDz = __ldg(ket.AB + 2 * (size_t)ket.npair + ik_);
+    }
+    const int nkc = __ldg(ket.nprim + ik_);
     if constexpr (PS == 1) {
         for (int kc = 0; kc < nkc; ++kc) {
             double q, Qx, Qy, Qz, cQ;
@@ -621,20 +611,19 @@ __device__ __forceinline__ int scan_kets(const PairGroup& ket, const double tau,
     if (tau > 0.0) {
         double qcd[SW];
         float dcd[SW];
-        int ss[SW];
+        int sc[SW], sd[SW];
 #pragma unroll
         for (int j = 0; j < SW; ++j) {
             const int ikc = scan + j * 32 + lane;
             ok[j] = ikc < nket;
             const int ii = ok[j] ? ikc : scan;          // scan < nket: always a valid index
             qcd[j] = __ldg(ket.Q + ii); dcd[j] = __ldg(ket.Dp + ii);
-            ss[j] = __ldg(ket.ssp + ii);
+            sc[j] = __ldg(ket.sa + ii); sd[j] = __ldg(ket.sb + ii);
         }
 #pragma unroll
         for (int j = 0; j < SW; ++j) {
             float dm = fmaxf(dab, dcd[j]);
-            const int sc = ss[j] & 0xffff, sd = ss[j] >> 16;
-            const float dk = fmaxf(fmaxf(dsh_a[sc], dsh_a[sd]), fmaxf(dsh_b[sc], dsh_b[sd]));
+            const float dk = fmaxf(fmaxf(dsh_a[sc[j]], dsh_a[sd[j]]), fmaxf(dsh_b[sc[j]], dsh_b[sd[j]]));
             dm = fmaxf(dm, 0.5f * dk);
             ok[j] = ok[j] && !(qab * qcd[j] * (double)dm < tau);
         }
@@ -677,11 +666,8 @@ template <int PS> struct BlockCfg {
     static constexpr int SW = PS == 1 ? QCF_SCANW : 1;        // scan width: a PS > 1 warp consumes only 32/PS quartets per pass
     static constexpr int QLEN = 32 * (SW + 1);
 };
-#ifndef QCF_MINBLOCKS
-#define QCF_MINBLOCKS 1
-#endif
 template <int LA, int LB, int LC, int LD, int NK, int PS>
-__global__ void __launch_bounds__(128, QCF_MINBLOCKS)
+__global__ void __launch_bounds__(128)
 eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     using KA = KAcc<LA, LB, LC, LD>;
     constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
@@ -695,15 +681,15 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     const double fx = a.sc->fx_scale;
 
     const int N = a.N;
-    const int4 mb = ldg_meta(bra.meta + ib_);
-    const int fa = mb.x, fb = mb.y, sa = mb.z & 0xffff, sb = mb.z >> 16;
+    const int fa = __ldg(bra.fa + ib_), fb = __ldg(bra.fb + ib_);
+    const int sa = __ldg(bra.sa + ib_), sb = __ldg(bra.sb + ib_);
     const double bra_deg = (sa == sb) ? 0.5 : 1.0;
     const float dab = __ldg(bra.Dp + ib_);
 
     // CTA-constant data in shared memory: the bra primitives and the two rows (shell a, shell b) of the
     // shell-block density maxima that the exchange screening gathers from
     extern __shared__ __align__(16) double dyn_s[];
-    const int nkb = mb.w;
+    const int nkb = __ldg(bra.nprim + ib_);
     double* const bra_s = dyn_s;                                                     // [bra.K][BRA_S]
     float* const dsh_a = reinterpret_cast<float*>(dyn_s + (size_t)bra.K * BRA_S);    // [nshell]
     float* const dsh_b = dsh_a + a.nshell;                                           // [nshell]
@@ -714,7 +700,9 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
             dsh_b[t] = __ldg(a.Dsh + (size_t)sb * a.nshell + t);
         }
     double ABx = 0, ABy = 0, ABz = 0;
-    if constexpr (LB > 0) load_AB(bra, ib_, ABx, ABy, ABz);
+    if constexpr (LB > 0) {
+        ABx = __ldg(bra.AB + ib_); ABy = __ldg(bra.AB + bra.npair + ib_); ABz = __ldg(bra.AB + 2 * (size_t)bra.npair + ib_);
+    }
     __syncthreads();
 
     double jab[NAB];
@@ -745,14 +733,14 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
         const unsigned int amask = __ballot_sync(0xffffffffu, slot < nrun);
         if (slot < nrun) {
         const int ik_ = queue[qn - nrun + slot];
-        const int4 mk = ldg_meta(ket.meta + ik_);
-        const int fc = mk.x, fd = mk.y;
+        const int sc = __ldg(ket.sa + ik_), sd = __ldg(ket.sb + ik_);
         if (sub == 0) ++nq;
-        double deg = bra_deg * (((mk.z & 0xffff) == (mk.z >> 16)) ? 0.5 : 1.0);
+        const int fc = __ldg(ket.fa + ik_), fd = __ldg(ket.fb + ik_);
+        double deg = bra_deg * ((sc == sd) ? 0.5 : 1.0);
         if (same_group && ik_ == ib_) deg *= 0.5;
 
         double I[NI];
-        contracted_quartet_staged<LA, LB, LC, LD, PS>(bra_s, nkb, ABx, ABy, ABz, ket, ik_, mk.w, deg, a.boys, sub, amask, I);
+        contracted_quartet_staged<LA, LB, LC, LD, PS>(bra_s, nkb, ABx, ABy, ABz, ket, ik_, deg, a.boys, sub, amask, I);
 
         if (sub == 0) {
         double kacc[NK * KA::SIZE];

@@ -255,9 +255,9 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     if (nket <= ket0) return;
     const double fx = a.sc->fx_scale;
 
-    const int4 mb = ldg_meta(bra.meta + ib_);
-    const int N = a.N, KAB = mb.w;
-    const int fa = mb.x, fb = mb.y, sa = mb.z & 0xffff, sb = mb.z >> 16;
+    const int N = a.N, KAB = __ldg(bra.nprim + ib_);
+    const int fa = __ldg(bra.fa + ib_), fb = __ldg(bra.fb + ib_);
+    const int sa = __ldg(bra.sa + ib_), sb = __ldg(bra.sb + ib_);
     const double bra_deg = (sa == sb) ? 0.5 : 1.0;
     const float dab = __ldg(bra.Dp + ib_);
 
@@ -267,12 +267,15 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     double* const jab_all = pab_s + ((NAB + 1) & ~1);          // [NAB][BLOCK] when JSMEM
     {
         double ABx = 0, ABy = 0, ABz = 0;
-        if constexpr (LB > 0) load_AB(bra, ib_, ABx, ABy, ABz);
+        if constexpr (LB > 0) {
+            ABx = __ldg(bra.AB + ib_); ABy = __ldg(bra.AB + bra.npair + ib_); ABz = __ldg(bra.AB + 2 * (size_t)bra.npair + ib_);
+        }
         for (int t = threadIdx.x; t < 3 * KAB; t += BLOCK) {
             const int kb = t / 3, axis = t % 3;
-            const double* base = bra.prim + ((size_t)kb * bra.npair + ib_) * PF_COUNT;
-            const double p = __ldg(base + PF_P);
-            const double xpa = __ldg(base + PF_PAX + axis);
+            const double* base = bra.prim + (size_t)kb * PF_COUNT * bra.npair + ib_;
+            const size_t np = bra.npair;
+            const double p = __ldg(base + PF_P * np);
+            const double xpa = __ldg(base + (PF_PAX + axis) * np);
             const double ab = axis == 0 ? ABx : (axis == 1 ? ABy : ABz);
             EAxis<LA, LB> E;
 #pragma unroll
@@ -282,8 +285,8 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
 #pragma unroll
             for (int i = 0; i < EL::EA_N; ++i) dst[EL::PRIM + axis * EL::EA_N + i] = E.e[i];
             if (axis == 0) {
-                dst[0] = p; dst[1] = __ldg(base + PF_PX); dst[2] = __ldg(base + PF_PY);
-                dst[3] = __ldg(base + PF_PZ); dst[4] = __ldg(base + PF_C);
+                dst[0] = p; dst[1] = __ldg(base + PF_PX * np); dst[2] = __ldg(base + PF_PY * np);
+                dst[3] = __ldg(base + PF_PZ * np); dst[4] = __ldg(base + PF_C * np);
             }
         }
         for (int i = threadIdx.x; i < NAB; i += BLOCK) pab_s[i] = __ldg(a.Pj + (size_t)(fa + i / NB) * N + fb + i % NB);
@@ -344,14 +347,16 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
         if (nrun == 0) break;
         if (lane < nrun) {
         const int ik_ = ket_queue[ksub][qn - nrun + lane];
-        const int4 mk = ldg_meta(ket.meta + ik_);
-        const int fc = mk.x, fd = mk.y;
+        const int sc = __ldg(ket.sa + ik_), sd = __ldg(ket.sb + ik_);
         if (sg == 0) ++nq;
-        double deg = bra_deg * (((mk.z & 0xffff) == (mk.z >> 16)) ? 0.5 : 1.0);
+        const int fc = __ldg(ket.fa + ik_), fd = __ldg(ket.fb + ik_);
+        double deg = bra_deg * ((sc == sd) ? 0.5 : 1.0);
         if (same_group && ik_ == ib_) deg *= 0.5;
         double CDx = 0, CDy = 0, CDz = 0;
-        if constexpr (LD > 0) load_AB(ket, ik_, CDx, CDy, CDz);
-        const int nkc = mk.w;
+        if constexpr (LD > 0) {
+            CDx = __ldg(ket.AB + ik_); CDy = __ldg(ket.AB + ket.npair + ik_); CDz = __ldg(ket.AB + 2 * (size_t)ket.npair + ik_);
+        }
+        const int nkc = __ldg(ket.nprim + ik_);
         for (int kb = 0; kb < KAB; ++kb) {
             const double* __restrict__ tb = tab + (size_t)kb * EL::STRIDE;
             const double p = tb[0], Px = tb[1], Py = tb[2], Pz = tb[3], cP = tb[4] * deg;

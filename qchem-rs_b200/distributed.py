@@ -1,11 +1,15 @@
 """Multi-GPU Fock build: one process per GPU, a static split of the bra-pair list, one allreduce.
 
 SURVEY.md 8e: shell quartets are independent, only the N x N accumulators are shared.  Every rank holds
-the full pair data and a full replica of P, evaluates the bra pairs i with i % world_size == rank of every
-(class, primitive-count) group -- the groups are sorted by Schwarz bound, so the interleaved split is
-balanced in modelled cost -- and produces a PARTIAL G.  The partials are summed with a single
-`all_reduce(SUM)` (NCCL over NVLink on the GPU box; gloo in the CPU tests).  There is no other
-communication on the path.
+the full pair data and a full replica of P, evaluates its share of every (class, primitive-count) group's
+bra-pair list -- a static split balanced by modelled cost (primitive quartets x class op count x length of
+the Schwarz prefix; qcf_opts.rank / world_size, engine.cu make_plan) -- and produces a PARTIAL G.  The
+partials are summed with a single `all_reduce(SUM)` (NCCL over NVLink on the GPU box; gloo in the CPU
+tests).  There is no other communication on the path.
+
+This module is the multi-PROCESS route (one process per GPU, torchrun).  The single-process route -- one
+context created with qcf_opts.n_gpus = N driving all GPUs from one host thread, partial matrices summed over
+NVLink peer memory inside the finalize kernel -- lives entirely inside libqcfock.so (`FockEngine(n_gpus=N)`).
 
 The reduce step is written against `torch.distributed` only, so the host-side logic (partition +
 reduction) is testable on CPU with world_size 2 and any object that has `partial_rhf` / `partial_uhf`.

@@ -46,7 +46,8 @@ def main():
     bs = pkg.BasisSet.load(ROOT / "data" / "basis" / "6-31G_st.json")
     system = pkg.MolecularSystem.from_atoms(pkg.molecules.water_cluster(n), bs)
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
-    with pkg.engine.FockEngine(system, tau=1e-12) as eng:
+    ngpus = int(os.environ.get("AB_NGPUS", "1"))
+    with pkg.engine.FockEngine(system, tau=1e-12, n_gpus=ngpus) as eng:
         P = density(system, eng, n)
         ms, e2e, host = [], [], []
         for r in range(reps + 2):
@@ -59,7 +60,8 @@ def main():
         tf = st["model_flops"] / (np.median(ms) * 1e-3) / 1e12
         print(f"AB {tag} n={n} N={eng.n} kernel_ms min={min(ms):.3f} med={np.median(ms):.3f} e2e_med={np.median(e2e):.3f} "
               f"host_ms={np.median(host):.3f} quartets={st['quartets']:.4e} modelTF={tf:.2f} frac={tf / peak:.3f} peak={peak:.2f} "
-              f"launches={st['launches']} graph={st['graph_launches']} create_ms={st['create_ms']:.0f}", flush=True)
+              f"launches={st['launches']} graph={st['graph_launches']} create_ms={st['create_ms']:.0f} "
+              f"ngpus={ngpus} device_ms={[round(x, 2) for x in eng.device_times()]} imbalance_model={st['rank_imbalance']:.4f}", flush=True)
         if topn and os.environ.get("QCF_PROFILE") == "1":
             recs = eng.launch_profile()
             tot = sum(r["ms"] for r in recs)
