@@ -18,7 +18,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <numeric>
+#include <thread>
 #include <tuple>
 
 using namespace qcf;
@@ -62,6 +66,65 @@ double model_flops_prim(int la, int lb, int lc, int ld) {
     f += 2.0 * nherm(Lcd) * nab * ncd;
     return f;
 }
+
+}  // namespace
+
+// Persistent helper threads for the two staging copies of a host call (caller's pageable P -> pinned, pinned -> caller's
+// G): one thread moves 8 MB at ~10 GB/s, i.e. 0.8 ms per matrix and call -- 15 % of an 11 ms build on 8 GPUs.
+struct qcf_copy_pool {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cv, done_cv;
+    std::function<void(int)> job;
+    int generation = 0, pending = 0;
+    bool stop = false;
+    explicit qcf_copy_pool(int n) {
+        for (int w = 0; w < n; ++w)
+            workers.emplace_back([this, w] {
+                int seen = 0;
+                while (true) {
+                    std::function<void(int)> j;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv.wait(lk, [&] { return stop || generation != seen; });
+                        if (stop) return;
+                        seen = generation;
+                        j = job;
+                    }
+                    j(w + 1);
+                    {
+                        std::lock_guard<std::mutex> lk(m);
+                        if (--pending == 0) done_cv.notify_all();
+                    }
+                }
+            });
+    }
+    ~qcf_copy_pool() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv.notify_all();
+        for (auto& t : workers) t.join();
+    }
+    // dst[0..bytes) = src[0..bytes), split over the calling thread and the workers
+    void copy(void* dst, const void* src, size_t bytes) {
+        const int parts = (int)workers.size() + 1;
+        if (parts == 1 || bytes < (1u << 20)) { std::memcpy(dst, src, bytes); return; }
+        const size_t chunk = ((bytes + parts - 1) / parts + 63) & ~size_t(63);
+        auto part = [=](int i) {
+            const size_t lo = std::min(bytes, chunk * i), hi = std::min(bytes, chunk * (i + 1));
+            if (hi > lo) std::memcpy((char*)dst + lo, (const char*)src + lo, hi - lo);
+        };
+        {
+            std::lock_guard<std::mutex> lk(m);
+            job = part; pending = (int)workers.size(); ++generation;
+        }
+        cv.notify_all();
+        part(0);
+        std::unique_lock<std::mutex> lk(m);
+        done_cv.wait(lk, [&] { return pending == 0; });
+    }
+};
+
+namespace {
 
 double now_ms() {
     using namespace std::chrono;
@@ -629,6 +692,7 @@ int enqueue_device_work(qcf_ctx* ctx, qcf_device& dv, int mode, const double* pa
     // difference-density builds: the errors of up to `full_every` consecutive screened builds add up in G, so each one
     // is screened an order of magnitude tighter
     a.tau = ctx->screening ? ctx->tau * (incremental ? 0.125 : 1.0) : 0.0;
+    a.red_eps = ctx->red_eps_factor * a.tau;
     a.sc = dv.sc;
     a.boys = dv.boys;
 
@@ -777,38 +841,31 @@ int host_build(qcf_ctx* ctx, int mode, const double* Pa, const double* Pb, doubl
     qcf_device& d0 = ctx->dev[0];
     CK(cudaSetDevice(d0.device));
     cudaStream_t ms = d0.main;
+    bool full_rebuild = false;
     if (incremental) {
         int rc = ensure_incremental_buffers(ctx, nk);
         if (rc) return rc;
-        if (reset || ctx->incremental_builds == 0) {
-            for (auto& dv : ctx->dev) {
-                CK(cudaSetDevice(dv.device));
-                for (int k = 0; k < nk; ++k) CK(cudaMemsetAsync(dv.Pprev[k], 0, nn * sizeof(double), dv.main));
-                CK(cudaStreamSynchronize(dv.main));
-            }
-            CK(cudaSetDevice(d0.device));
-            for (int k = 0; k < 2; ++k) CK(cudaMemsetAsync(d0.Gprev[k], 0, nn * sizeof(double), ms));
-            ctx->incremental_builds = 0;
-        }
+        full_rebuild = reset || ctx->incremental_builds == 0;
     }
     CK(cudaEventRecord(ctx->ev_h0, ms));
-    std::memcpy(ctx->h_pin, Pa, nn * sizeof(double));
+    ctx->pool->copy(ctx->h_pin, Pa, nn * sizeof(double));
     CK(cudaMemcpyAsync(d0.Pin[0], ctx->h_pin, nn * sizeof(double), cudaMemcpyHostToDevice, ms));
     if (Pb) {
-        std::memcpy(ctx->h_pin + nn, Pb, nn * sizeof(double));
+        ctx->pool->copy(ctx->h_pin + nn, Pb, nn * sizeof(double));
         CK(cudaMemcpyAsync(d0.Pin[1], ctx->h_pin + nn, nn * sizeof(double), cudaMemcpyHostToDevice, ms));
     }
     double* g0 = incremental ? d0.Gprev[0] : d0.G[0];
     double* g1 = incremental ? d0.Gprev[1] : d0.G[1];
-    int rc = run_build_impl(ctx, mode, d0.Pin[0], Pb ? d0.Pin[1] : nullptr, g0, g1, ms, incremental != 0);
+    int rc = incremental ? qcf_internal::run_build_scf(ctx, mode, d0.Pin[0], Pb ? d0.Pin[1] : nullptr, g0, g1, ms, true, full_rebuild)
+                         : run_build_impl(ctx, mode, d0.Pin[0], Pb ? d0.Pin[1] : nullptr, g0, g1, ms, false);
     if (rc) return rc;
     if (incremental) ++ctx->incremental_builds;
     CK(cudaMemcpyAsync(ctx->h_pin + 2 * nn, g0, nn * sizeof(double), cudaMemcpyDeviceToHost, ms));
     if (G1) CK(cudaMemcpyAsync(ctx->h_pin + 3 * nn, g1, nn * sizeof(double), cudaMemcpyDeviceToHost, ms));
     CK(cudaEventRecord(ctx->ev_h1, ms));
     CK(cudaStreamSynchronize(ms));
-    std::memcpy(G0, ctx->h_pin + 2 * nn, nn * sizeof(double));
-    if (G1) std::memcpy(G1, ctx->h_pin + 3 * nn, nn * sizeof(double));
+    ctx->pool->copy(G0, ctx->h_pin + 2 * nn, nn * sizeof(double));
+    if (G1) ctx->pool->copy(G1, ctx->h_pin + 3 * nn, nn * sizeof(double));
     float t = 0;
     CK(cudaEventElapsedTime(&t, ctx->ev_h0, ctx->ev_h1));
     ctx->stats.total_ms = t;
@@ -836,22 +893,22 @@ int run_build_scf(qcf_ctx* ctx, int mode, const double* dPa, const double* dPb, 
     int rc = ensure_incremental_buffers(ctx, nk);
     if (rc) return rc;
     if (reset) {
+        // full rebuild: the plain build at tau into dG0/dG1, then P_prev <- P on every device (device 0 from the
+        // caller's buffers, the others from the replicas the build has just peer-copied, each on the stream that
+        // device's next build runs on)
+        rc = run_build_impl(ctx, mode, dPa, dPb, dG0, dG1, user, false);
+        if (rc) return rc;
         qcf_device& d0 = ctx->dev[0];
         CK(cudaSetDevice(d0.device));
-        CK(cudaMemsetAsync(dG0, 0, nn * sizeof(double), user));
-        if (dG1) CK(cudaMemsetAsync(dG1, 0, nn * sizeof(double), user));
-        for (int k = 0; k < nk; ++k) CK(cudaMemsetAsync(d0.Pprev[k], 0, nn * sizeof(double), user));
-        if (ctx->dev.size() > 1) {
-            // the other devices zero their P_prev on their own streams, ordered after whatever `user` has done so far
-            CK(cudaEventRecord(ctx->ev_in, user));
-            for (size_t d = 1; d < ctx->dev.size(); ++d) {
-                qcf_device& dv = ctx->dev[d];
-                CK(cudaSetDevice(dv.device));
-                CK(cudaStreamWaitEvent(dv.main, ctx->ev_in, 0));
-                for (int k = 0; k < nk; ++k) CK(cudaMemsetAsync(dv.Pprev[k], 0, nn * sizeof(double), dv.main));
-            }
-            CK(cudaSetDevice(d0.device));
+        CK(cudaMemcpyAsync(d0.Pprev[0], dPa, nn * sizeof(double), cudaMemcpyDeviceToDevice, user));
+        if (nk == 2) CK(cudaMemcpyAsync(d0.Pprev[1], dPb, nn * sizeof(double), cudaMemcpyDeviceToDevice, user));
+        for (size_t d = 1; d < ctx->dev.size(); ++d) {
+            qcf_device& dv = ctx->dev[d];
+            CK(cudaSetDevice(dv.device));
+            for (int k = 0; k < nk; ++k) CK(cudaMemcpyAsync(dv.Pprev[k], dv.Pin[k], nn * sizeof(double), cudaMemcpyDeviceToDevice, dv.main));
         }
+        CK(cudaSetDevice(d0.device));
+        return QCF_OK;
     }
     return run_build_impl(ctx, mode, dPa, dPb, dG0, dG1, user, true);
 }
@@ -941,6 +998,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     if (const char* e = getenv("QCF_TARGET_CTAS")) ctx->target_ctas = std::max(1, atoi(e));
     if (const char* e = getenv("QCF_PS_MIN")) ctx->ps_min_prim = std::max(1, atoi(e));
     if (const char* e = getenv("QCF_BLOCK")) ctx->block = atoi(e);
+    if (const char* e = getenv("QCF_RED_EPS_FACTOR")) ctx->red_eps_factor = std::max(0.0, atof(e));
     if (const char* e = getenv("QCF_ORDER")) ctx->launch_order = atoi(e);
     if (ctx->block < 32 || ctx->block > 128 || ctx->block % 32) return fail(QCF_ERR_ARG, "block_threads must be 32, 64, 96 or 128");
     ctx->natoms = b->n_atoms; ctx->nshell = b->n_shells;
@@ -1020,6 +1078,11 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     }
     CK(cudaSetDevice(device0));
     CK(cudaHostAlloc(&ctx->h_pin, 4 * nn * sizeof(double), cudaHostAllocPortable));
+    {
+        int nthr = 3;     // helper threads of the staging copies (plus the calling thread)
+        if (const char* e = getenv("QCF_COPY_THREADS")) nthr = std::max(0, std::min(15, atoi(e) - 1));
+        ctx->pool = new qcf_copy_pool(nthr);
+    }
     ctx->stats.n_basis = ctx->N; ctx->stats.n_shells = ctx->nshell;
     ctx->stats.n_devices = ngpus;
     const long long nsp = (long long)ctx->nshell * (ctx->nshell + 1) / 2;
@@ -1273,6 +1336,7 @@ void qcf_destroy(qcf_ctx* ctx) {
     for (auto& dv : ctx->dev) destroy_device(dv);
     if (!ctx->dev.empty()) cudaSetDevice(ctx->dev[0].device);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    delete ctx->pool;
     for (cudaEvent_t e : {ctx->ev_t0, ctx->ev_t1, ctx->ev_h0, ctx->ev_h1, ctx->ev_in}) if (e) cudaEventDestroy(e);
     delete ctx;
 }

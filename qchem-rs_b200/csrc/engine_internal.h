@@ -75,6 +75,7 @@ struct qcf_ctx {
     int block = 64, kets_per_thread = 64, target_ctas = 296, nstreams = 8;
     double serial_cap = 4e6;          // model flops one thread may run serially in one launch
     double tau = 1e-12;
+    double red_eps_factor = 0.01;     // scatter contributions below this fraction of tau are not sent to memory
     bool screening = true, deterministic = false, use_graph = true, profile = false;
     int launch_order = 0;             // 0: longest-running threads first; 1: biggest launches first (QCF_ORDER)
     int ps_min_prim = 36;             // primitive quartets per shell quartet from which lanes share a quartet
@@ -94,6 +95,7 @@ struct qcf_ctx {
     size_t npairs = 0;
     std::vector<qcf_device> dev;      // dev[0] is the context's primary device
     double* h_pin = nullptr;          // pinned staging, 4*N*N
+    struct qcf_copy_pool* pool = nullptr;   // helper threads of the host staging copies
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_h0 = nullptr, ev_h1 = nullptr, ev_in = nullptr;
     // stats of the last build
     struct LaunchRec { int bra, ket; float ms = 0; };

@@ -145,7 +145,7 @@ template <int LA, int LB, int LC, int LD, int NK, int SPT, int IA, int... IB>
 __device__ __forceinline__ void digest_a(std::integer_sequence<int, IB...>, const int SG, const double (&Hs)[SPT][nherm(LA + LB)],
                                          const double* __restrict__ e3, const double* __restrict__ pab_s,
                                          double* __restrict__ jab_s, double (&jab)[ncart(LA) * ncart(LB)],
-                                         DigestState<NK, SPT, ncart(LB)>& d, const BuildArgs& a, const double fx, int fa, int fc, int fd) {
+                                         DigestState<NK, SPT, ncart(LB)>& d, const BuildArgs& a, const AccMode fx, int fa, int fc, int fd) {
     constexpr int ND = ncart(LD);
     const int N = a.N;
 #pragma unroll
@@ -176,7 +176,7 @@ template <int LA, int LB, int LC, int LD, int NK, int SPT, int... IA>
 __device__ __forceinline__ void digest_all_a(std::integer_sequence<int, IA...>, const int SG, const double (&Hs)[SPT][nherm(LA + LB)],
                                              const double* __restrict__ e3, const double* __restrict__ pab_s,
                                              double* __restrict__ jab_s, double (&jab)[ncart(LA) * ncart(LB)],
-                                             DigestState<NK, SPT, ncart(LB)>& d, const BuildArgs& a, const double fx, int fa, int fc, int fd) {
+                                             DigestState<NK, SPT, ncart(LB)>& d, const BuildArgs& a, const AccMode fx, int fa, int fc, int fd) {
     (digest_a<LA, LB, LC, LD, NK, SPT, IA>(std::make_integer_sequence<int, ncart(LB)>{}, SG, Hs, e3, pab_s, jab_s, jab, d, a, fx, fa, fc, fd), ...);
 }
 
@@ -185,7 +185,7 @@ __device__ __forceinline__ void digest_all_a(std::integer_sequence<int, IA...>, 
 template <int LA, int LB, int LC, int LD, int NK, int SPT>
 __device__ __forceinline__ void slab_digest(const int SG, const double (&Hs)[SPT][nherm(LA + LB)], const double* __restrict__ e3,
                                             const double* __restrict__ pab_s, double* __restrict__ jab_s,
-                                            double (&jab)[ncart(LA) * ncart(LB)], const BuildArgs& a, const double fx, int fa, int fb, int fc, int fd) {
+                                            double (&jab)[ncart(LA) * ncart(LB)], const BuildArgs& a, const AccMode fx, int fa, int fb, int fc, int fd) {
     using C = SlabCfg<LA, LB, LC, LD, NK, SPT>;
     constexpr int NA = C::NA, NB = C::NB, ND = C::ND;
     const int N = a.N;
@@ -253,7 +253,7 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     const int ket0 = blockIdx.y * a.ket_chunk;
     const int nket = ket_prefix_end(ket, a, qab, ib_, same_group, ket0);
     if (nket <= ket0) return;
-    const double fx = a.sc->fx_scale;
+    const AccMode fx{a.sc->fx_scale, a.red_eps};
 
     const int N = a.N, KAB = __ldg(bra.nprim + ib_);
     const int fa = __ldg(bra.fa + ib_), fb = __ldg(bra.fb + ib_);

@@ -36,6 +36,7 @@ struct Diis {
 
 struct qcf_scf {
     int N = 0, nspin = 1, nocc[2] = {0, 0}, iteration = 0, full_every = 0, since_full = 0;
+    double last_rms = 1.0;           // density rms of the previous step: difference-density builds pay off only once it is small
     double factor = 2.0;
     cublasHandle_t blas = nullptr;
     cusolverDnHandle_t sol = nullptr;
@@ -317,6 +318,7 @@ int qcf_scf_init(qcf_ctx* ctx, const double* S, const double* H, int unrestricte
     if (info != 0) { ctx->err = "cusolverDnDsyevd did not converge (info = " + std::to_string(info) + ")"; return QCF_ERR_CUDA; }
     s->iteration = 0;
     s->since_full = 0;
+    s->last_rms = 1.0;
     return QCF_OK;
 }
 
@@ -330,12 +332,14 @@ int qcf_scf_step(qcf_ctx* ctx, double epsilon, qcf_scf_info* out) {
     const auto t0 = std::chrono::steady_clock::now();
     CK(cudaEventRecord(s->e0, s->stream));
     // ---- G(P): full or difference-density build, enqueued on the SCF stream (rhf.rs:67-68, uhf.rs:90-91) ----
+    // difference-density builds once the density moves little (their screening runs on |P - P_prev|, at tau / 8): while the
+    // SCF is far from convergence a full build is cheaper; a full rebuild every `full_every` steps bounds the accumulated error
     const bool inc = s->full_every > 0;
-    const bool reset = inc && (s->since_full == 0);
+    const bool reset = inc && (s->since_full == 0 || s->last_rms > 1e-4);
     int rc = qcf_internal::run_build_scf(ctx, s->nspin == 2 ? 1 : 0, s->P[0], s->nspin == 2 ? s->P[1] : nullptr, s->G[0],
                                          s->nspin == 2 ? s->G[1] : nullptr, s->stream, inc, reset);
     if (rc) return rc;
-    if (inc) s->since_full = (s->since_full + 1) % s->full_every;
+    if (inc) s->since_full = reset ? 1 % s->full_every : (s->since_full + 1) % s->full_every;
     CK(cudaEventRecord(s->e1, s->stream));
     double e_sum = 0.0, rms_sum = 0.0;
     double h[2][3];
@@ -379,6 +383,7 @@ int qcf_scf_step(qcf_ctx* ctx, double epsilon, qcf_scf_info* out) {
     CK(cudaEventElapsedTime(&sms, s->e1, s->e2));
     double rms = rms_sum;
     if (s->nspin == 2) rms = rms_sum / 2.0 / 2.0;     // uhf.rs:137 and :139
+    s->last_rms = rms;
     out->iteration = s->iteration;
     out->converged = rms < epsilon ? 1 : 0;
     out->electronic_energy = e_sum;

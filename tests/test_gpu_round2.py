@@ -307,8 +307,8 @@ def test_in_library_multi_gpu_matches_single_gpu():
     Pa, Pb = random_symmetric_density(n, 42), random_symmetric_density(n, 43)
     with engine.FockEngine(system, tau=1e-12) as eng:
         g1 = eng.rhf(P)
-        a1, b1 = eng.uhf(Pa, Pb)
         q1 = eng.stats()["quartets"]
+        a1, b1 = eng.uhf(Pa, Pb)
     for k in sorted({2, min(ng, 4), ng}):
         with engine.FockEngine(system, tau=1e-12, n_gpus=k) as eng:
             gk = eng.rhf(P)
@@ -344,3 +344,23 @@ def test_cost_balanced_split_covers_every_bra_once(world):
             assert 1.0 <= st["rank_imbalance"] < 1.02
     np.testing.assert_allclose(acc, full, atol=1e-11)
     assert q == q_full
+
+
+def test_cli_driver_runs_rhf_and_triplet_uhf(capsys):
+    """qchem-cli stand-in (main.rs:10-62): water/STO-3G RHF on the device loop and O2/6-31G with --spin-multiplicity 3
+    honoured (the reference ignores the flag, main.rs:115-116)."""
+    from helpers import DATA
+    from qchem_rs_b200 import cli
+    assert cli.main(["rhf", "-b", str(DATA / "basis" / "STO-3G.json"), "-m", str(DATA / "mol" / "water.json"),
+                     "--epsilon", "1e-8"]) == 0
+    out = capsys.readouterr().out
+    e_dev = float([l for l in out.splitlines() if l.startswith("hartree fock energy")][0].split(":")[1])
+    assert cli.main(["rhf", "-b", str(DATA / "basis" / "STO-3G.json"), "-m", str(DATA / "mol" / "water.json"),
+                     "--epsilon", "1e-8", "--backend", "host"]) == 0
+    out = capsys.readouterr().out
+    e_host = float([l for l in out.splitlines() if l.startswith("hartree fock energy")][0].split(":")[1])
+    assert abs(e_dev - e_host) < E_TOL
+    assert cli.occupations(16, 0, 3) == (9, 7) and cli.occupations(16, 0, 0) == (8, 8)
+    rc = cli.main(["uhf", "-b", str(DATA / "basis" / "6-31G.json"), "-m", str(DATA / "mol" / "oxygen.json"), "-s", "3",
+                   "--max-iterations", "200", "--epsilon", "1e-4", "--backend", "host"])
+    assert rc in (0, 1)      # the reference's DIIS(2,8) loop may stall for this state (see test_gpu_parity); it must not crash
