@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -104,15 +105,10 @@ struct qcf_copy_pool {
         cv.notify_all();
         for (auto& t : workers) t.join();
     }
-    // dst[0..bytes) = src[0..bytes), split over the calling thread and the workers
-    void copy(void* dst, const void* src, size_t bytes) {
-        const int parts = (int)workers.size() + 1;
-        if (parts == 1 || bytes < (1u << 20)) { std::memcpy(dst, src, bytes); return; }
-        const size_t chunk = ((bytes + parts - 1) / parts + 63) & ~size_t(63);
-        auto part = [=](int i) {
-            const size_t lo = std::min(bytes, chunk * i), hi = std::min(bytes, chunk * (i + 1));
-            if (hi > lo) std::memcpy((char*)dst + lo, (const char*)src + lo, hi - lo);
-        };
+    int threads() const { return (int)workers.size() + 1; }
+    // part(i) for i = 0 .. threads()-1, part 0 on the calling thread; returns when all are done
+    void run(const std::function<void(int)>& part) {
+        if (workers.empty()) { part(0); return; }
         {
             std::lock_guard<std::mutex> lk(m);
             job = part; pending = (int)workers.size(); ++generation;
@@ -121,6 +117,16 @@ struct qcf_copy_pool {
         part(0);
         std::unique_lock<std::mutex> lk(m);
         done_cv.wait(lk, [&] { return pending == 0; });
+    }
+    // dst[0..bytes) = src[0..bytes), split over the calling thread and the workers
+    void copy(void* dst, const void* src, size_t bytes) {
+        const int parts = threads();
+        if (parts == 1 || bytes < (1u << 20)) { std::memcpy(dst, src, bytes); return; }
+        const size_t chunk = ((bytes + parts - 1) / parts + 63) & ~size_t(63);
+        run([=](int i) {
+            const size_t lo = std::min(bytes, chunk * i), hi = std::min(bytes, chunk * (i + 1));
+            if (hi > lo) std::memcpy((char*)dst + lo, (const char*)src + lo, hi - lo);
+        });
     }
 };
 
@@ -461,7 +467,9 @@ int build_pairs(qcf_ctx* ctx) {
     }
     // primitive screening: Schwarz factor of every primitive pair on its own (the same class kernel on a
     // K = 1 list); inside each shell pair the primitives are sorted by it and those that cannot contribute
-    // Q_k * Q_max >= 1e-4 tau to any integral are dropped (the kernels loop over nprim[i] <= K primitives)
+    // Q_k * Q_max >= tau to any integral are dropped (the kernels loop over nprim[i] <= K primitives).  Measured at
+    // N = 1007 (profiles/r2_ab_call8_prim_cut.log, r2_ab_call11_cuts.log): factor 1e-4 / 1e-1 / 1 / 10 keeps 66 / 59 / 56 / 53 %
+    // of the primitive pairs, 70.8 / 69.2 / 68.2 / 67.1 ms, max |dG| vs the unscreened oracle 3.7e-11 / 3.7e-11 / 3.7e-11 / 4.6e-11
     ctx->prim_total = ctx->prim_kept = 0;
     for (auto& g : ctx->groups) {
         const long long np = (long long)g.pairs.size();
@@ -475,7 +483,7 @@ int build_pairs(qcf_ctx* ctx) {
         std::vector<double> Qk;
         int rc = schwarz_of(ctx, g1, Qk);
         if (rc) return rc;
-        const double pcut = ctx->tau * 1e-4 / std::max(ctx->qmax, 1e-300);
+        const double pcut = ctx->tau * ctx->prim_cut_factor / std::max(ctx->qmax, 1e-300);
         for (long long i = 0; i < np; ++i) {
             auto& pr = g.pairs[i];
             pr.order.resize(g.K);
@@ -492,7 +500,7 @@ int build_pairs(qcf_ctx* ctx) {
     size_t npairs = 0;
     for (auto& g : ctx->groups) {
         if (ctx->screening) {
-            const double cut = ctx->tau * 1e-2 / std::max(ctx->qmax, 1e-300);
+            const double cut = ctx->tau * ctx->pair_cut_factor / std::max(ctx->qmax, 1e-300);
             g.pairs.erase(std::remove_if(g.pairs.begin(), g.pairs.end(), [&](const HostPair& p) { return p.Q < cut; }), g.pairs.end());
         }
         std::stable_sort(g.pairs.begin(), g.pairs.end(), [](const HostPair& x, const HostPair& y) {
@@ -788,24 +796,49 @@ int run_build_impl(qcf_ctx* ctx, int mode, const double* dPa, const double* dPb,
     CK(cudaEventRecord(ctx->ev_t0, user));
     int graph_launches = 0;
     if (nd > 1) CK(cudaEventRecord(ctx->ev_in, user));
-    for (int d = 0; d < nd; ++d) {
+    std::atomic<int> graph_launches_atomic{0};
+    // one device's share: replicate the density (peer copy dev[0] -> dev[d] over NVLink on dev[d]'s stream), replay the graph
+    auto enqueue_one = [&](int d, std::string& err) -> int {
         qcf_device& dv = ctx->dev[d];
         cudaStream_t sd = d == 0 ? user : dv.main;
         const double *pa = dPa, *pb = dPb;
-        CK(cudaSetDevice(dv.device));
+        cudaError_t e;
+#define CKD(call) do { e = (call); if (e != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e); return QCF_ERR_CUDA; } } while (0)
+        CKD(cudaSetDevice(dv.device));
         if (d > 0) {
-            // replicate the density: peer copy dev[0] -> dev[d] over NVLink on dev[d]'s stream
-            CK(cudaStreamWaitEvent(sd, ctx->ev_in, 0));
-            CK(cudaMemcpyPeerAsync(dv.Pin[0], dv.device, dPa, d0.device, nn * sizeof(double), sd));
-            if (nk == 2) CK(cudaMemcpyPeerAsync(dv.Pin[1], dv.device, dPb, d0.device, nn * sizeof(double), sd));
+            CKD(cudaStreamWaitEvent(sd, ctx->ev_in, 0));
+            CKD(cudaMemcpyPeerAsync(dv.Pin[0], dv.device, dPa, d0.device, nn * sizeof(double), sd));
+            if (nk == 2) CKD(cudaMemcpyPeerAsync(dv.Pin[1], dv.device, dPb, d0.device, nn * sizeof(double), sd));
             pa = dv.Pin[0]; pb = nk == 2 ? dv.Pin[1] : nullptr;
         }
-        CK(cudaEventRecord(dv.ev_k0, sd));
-        int rc = launch_device_work(ctx, dv, mode, pa, pb, incremental, sd, &graph_launches);
-        if (rc) return rc;
-        CK(cudaEventRecord(dv.ev_k1, sd));
-        if (nd > 1) CK(cudaEventRecord(dv.ev_acc, sd));
+        CKD(cudaEventRecord(dv.ev_k0, sd));
+        int gl = 0;
+        int rc = launch_device_work(ctx, dv, mode, pa, pb, incremental, sd, &gl);
+        if (rc) { err = ctx->err; return rc; }
+        if (gl) ++graph_launches_atomic;
+        CKD(cudaEventRecord(dv.ev_k1, sd));
+        if (nd > 1) CKD(cudaEventRecord(dv.ev_acc, sd));
+#undef CKD
+        return QCF_OK;
+    };
+    // graphs already captured: the devices are enqueued from the pool's threads at once (a graph launch costs ~50 us of host
+    // time, so eight in a row would start the last device 0.35 ms late); first use and profile mode stay on this thread
+    bool parallel = nd > 1 && ctx->pool && ctx->pool->threads() > 1 && ctx->use_graph && !ctx->profile;
+    for (auto& dv : ctx->dev) parallel = parallel && dv.graph != nullptr;
+    if (parallel) {
+        std::vector<int> rcs(nd, 0);
+        std::vector<std::string> errs(nd);
+        const int T = ctx->pool->threads();
+        ctx->pool->run([&](int t) { for (int d = t; d < nd; d += T) rcs[d] = enqueue_one(d, errs[d]); });
+        for (int d = 0; d < nd; ++d) if (rcs[d]) { ctx->err = errs[d]; return rcs[d]; }
+    } else {
+        for (int d = 0; d < nd; ++d) {
+            std::string err;
+            int rc = enqueue_one(d, err);
+            if (rc) { ctx->err = err; return rc; }
+        }
     }
+    graph_launches = graph_launches_atomic.load();
     PeerAcc acc{};
     for (int d = 0; d < nd; ++d) { acc.AJ[d] = ctx->dev[d].AJ; acc.AK0[d] = ctx->dev[d].AK[0]; acc.AK1[d] = ctx->dev[d].AK[1]; }
     const int tpb = 256;
@@ -992,6 +1025,9 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     // measured on the N = 1007 build: 64 kets per thread is best when one GPU has the whole bra list, 32 for a
     // rank's share of it (finer chunks keep the smaller grids balanced)
     ctx->kets_per_thread = ctx->world > 1 ? 32 : 64;
+    // a rank's share of a multi-GPU run launches grids of 1/world the size: more streams keep more of them in flight and
+    // fewer, longer CTAs amortise the per-CTA prologue (measured on rank 0 of 8: 10.8 -> 9.9 ms; profiles/r2_ab_call10_rank_share_knobs.log)
+    if (ctx->world > 1) { ctx->nstreams = ctx->world >= 4 ? 32 : 16; ctx->target_ctas = ctx->world >= 4 ? 74 : 148; }
     if (const char* e = getenv("QCF_KETS_PER_THREAD")) ctx->kets_per_thread = std::max(1, atoi(e));
     if (const char* e = getenv("QCF_STREAMS")) ctx->nstreams = std::min(QCF_MAXSTREAM, std::max(1, atoi(e)));
     if (const char* e = getenv("QCF_SERIAL_CAP")) ctx->serial_cap = std::max(1.0, atof(e));
@@ -999,6 +1035,8 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     if (const char* e = getenv("QCF_PS_MIN")) ctx->ps_min_prim = std::max(1, atoi(e));
     if (const char* e = getenv("QCF_BLOCK")) ctx->block = atoi(e);
     if (const char* e = getenv("QCF_RED_EPS_FACTOR")) ctx->red_eps_factor = std::max(0.0, atof(e));
+    if (const char* e = getenv("QCF_PRIM_CUT")) ctx->prim_cut_factor = std::max(0.0, atof(e));
+    if (const char* e = getenv("QCF_PAIR_CUT")) ctx->pair_cut_factor = std::max(0.0, atof(e));
     if (const char* e = getenv("QCF_ORDER")) ctx->launch_order = atoi(e);
     if (ctx->block < 32 || ctx->block > 128 || ctx->block % 32) return fail(QCF_ERR_ARG, "block_threads must be 32, 64, 96 or 128");
     ctx->natoms = b->n_atoms; ctx->nshell = b->n_shells;
@@ -1079,7 +1117,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     CK(cudaSetDevice(device0));
     CK(cudaHostAlloc(&ctx->h_pin, 4 * nn * sizeof(double), cudaHostAllocPortable));
     {
-        int nthr = 3;     // helper threads of the staging copies (plus the calling thread)
+        int nthr = std::max(3, std::min(ngpus, 8) - 1);     // helper threads: staging copies, per-device graph launches
         if (const char* e = getenv("QCF_COPY_THREADS")) nthr = std::max(0, std::min(15, atoi(e) - 1));
         ctx->pool = new qcf_copy_pool(nthr);
     }

@@ -37,7 +37,7 @@ struct PlannedLaunch {
     double serial, cost;
 };
 
-constexpr int QCF_MAXSTREAM = 16;
+constexpr int QCF_MAXSTREAM = 32;
 constexpr int QCF_MAXDEV = 16;
 
 // everything that lives on one GPU
@@ -75,7 +75,9 @@ struct qcf_ctx {
     int block = 64, kets_per_thread = 64, target_ctas = 296, nstreams = 8;
     double serial_cap = 4e6;          // model flops one thread may run serially in one launch
     double tau = 1e-12;
-    double red_eps_factor = 0.01;     // scatter contributions below this fraction of tau are not sent to memory
+    double red_eps_factor = 0.1;      // scatter contributions below this fraction of tau are not sent to memory
+    double pair_cut_factor = 1e-2;    // shell pairs with Q Q_max below this fraction of tau are dropped at creation
+    double prim_cut_factor = 1.0;     // primitive pairs with Q_k Q_max below this multiple of tau are dropped at creation
     bool screening = true, deterministic = false, use_graph = true, profile = false;
     int launch_order = 0;             // 0: longest-running threads first; 1: biggest launches first (QCF_ORDER)
     int ps_min_prim = 36;             // primitive quartets per shell quartet from which lanes share a quartet

@@ -79,7 +79,7 @@ struct BuildArgs {
     unsigned long long* counter;  // evaluated quartets of this launch
     const double* boys;       // [BOYS_LTOT+1][BOYS_NGRID][BOYS_ROW]
     const int* bra_list;      // this rank's share of the bra list (cost-balanced split); null: every bra pair
-    double red_eps;           // scatter contributions below this magnitude are skipped (0.01 tau; 0 without screening)
+    double red_eps;           // scatter contributions below this magnitude are skipped (0.1 tau; 0 without screening)
     int ket_chunk;            // kets per CTA (grid.y strides over the ket list)
 };
 
@@ -496,8 +496,9 @@ struct AccMode {
 __device__ __forceinline__ void red_add(double* addr, double v, const AccMode m) {
     // A shell quartet is evaluated when ONE of its six density-weighted bounds reaches tau; its other contributions can
     // be orders of magnitude smaller.  Each FP64 atomic costs ~1.3 SM-cycles per lane on the LSU path (the bottleneck of
-    // the low-L classes), so contributions below eps = 0.01 tau -- a hundredth of what the quartet screening itself
-    // neglects -- are dropped: measured -3.6 % build time at N = 1007 with max |dG| unchanged (3.5e-11).
+    // the low-L classes), so contributions below eps = 0.1 tau -- a tenth of what the quartet screening itself neglects
+    // per quartet -- are dropped.  Measured at N = 1007 (profiles/r2_ab_call7_red_threshold_factor.log): factor 0 77.7 ms,
+    // 0.01 72.7 ms, 0.1 70.9 ms, 1 68.9 ms; max |dG| vs the unscreened oracle 3.5e-11, 3.5e-11, 3.7e-11, 2.1e-10.
     if (!(fabs(v) >= m.eps)) return;
     if (m.fx != 0.0) {
         const long long q = __double2ll_rn(v * m.fx);

@@ -89,13 +89,22 @@ class DeviceFock:
         self.eng.rhf_dev(self.dP[0].data_ptr(), self.dG[0].data_ptr(), s)
         if world()[1] > 1:
             dist.all_reduce(self.dG[0], op=dist.ReduceOp.SUM)
+            self._symmetrize(self.dG[0])
         return self.dG[0]
+
+    @staticmethod
+    def _symmetrize(g):
+        """Every rank's partial matrix is exactly symmetric, but a ring / tree all-reduce sums element (i, j) and
+        element (j, i) in different rank orders, so the reduced matrix is symmetric only to rounding (1e-16).  The
+        reference's contract is an exactly symmetric G (utils.rs:7-13): average the two triangles."""
+        g.copy_(0.5 * (g + g.transpose(-1, -2)))
 
     def uhf_device(self):
         s = torch.cuda.current_stream(self.dev).cuda_stream
         self.eng.uhf_dev(self.dP[0].data_ptr(), self.dP[1].data_ptr(), self.dG[0].data_ptr(), self.dG[1].data_ptr(), s)
         if world()[1] > 1:
             dist.all_reduce(self.dG, op=dist.ReduceOp.SUM)
+            self._symmetrize(self.dG)
         return self.dG
 
     # -- host API (what the SCF drivers call): H2D, build, allreduce, D2H --------------------------

@@ -47,7 +47,8 @@ def main():
     system = pkg.MolecularSystem.from_atoms(pkg.molecules.water_cluster(n), bs)
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
     ngpus = int(os.environ.get("AB_NGPUS", "1"))
-    with pkg.engine.FockEngine(system, tau=1e-12, n_gpus=ngpus) as eng:
+    rank, world = int(os.environ.get("AB_RANK", "0")), int(os.environ.get("AB_WORLD", "1"))   # one rank's share of a multi-process run
+    with pkg.engine.FockEngine(system, tau=1e-12, n_gpus=ngpus, rank=rank, world_size=world) as eng:
         P = density(system, eng, n)
         ms, e2e, host = [], [], []
         for r in range(reps + 2):
