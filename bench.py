@@ -369,7 +369,8 @@ def run_b200(args):
         scf = {"epsilon": 1e-6}
         for name, o, dt in (("full_builds", out_dev, t1 - t0), ("incremental_every_8", out_inc, t3 - t2)):
             if o is not None:
-                scf[name] = {"iterations": o.iterations, "wall_s": dt, "e_total": o.total_energy(),
+                scf[name] = {"iterations": o.iterations, "wall_s": dt, "init_s": o.init_s,
+                             "steps_wall_s": sum(s["wall_ms"] for s in o.steps) * 1e-3, "e_total": o.total_energy(),
                              "build_ms": [round(s["build_ms"], 2) for s in o.steps],
                              "linalg_ms_mean": float(np.mean([s["linalg_ms"] for s in o.steps]))}
 

@@ -220,8 +220,11 @@ def restricted_hartree_fock_device(system, config: HartreeFockConfig, integrals,
                                    full_rebuild_every: int = 0) -> Optional[RestrictedHartreeFockOutput]:
     """rhf.rs:32-108 with the whole iteration on the GPU (qcf_scf_init / qcf_scf_step):
     P, G, F, the DIIS history and the orbitals stay in HBM; the host sees scalars only."""
+    import time
     S, T, V = integrals
+    t0 = time.perf_counter()
     engine.scf_init(S, T + V, system.n_electrons() // 2, unrestricted=False, full_rebuild_every=full_rebuild_every)
+    init_s = time.perf_counter() - t0
     nuclear_repulsion = compute_nuclear_repulsion(system.atoms)
     steps = []
     for _ in range(config.max_iterations + 1):
@@ -232,6 +235,7 @@ def restricted_hartree_fock_device(system, config: HartreeFockConfig, integrals,
                                               info["iteration"], engine.scf_get("density"), engine.scf_get("fock"),
                                               [s["build_ms"] * 1e-3 for s in steps])
             out.steps = steps
+            out.init_s = init_s
             return out
     return None
 
