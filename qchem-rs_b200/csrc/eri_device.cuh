@@ -112,7 +112,11 @@ __host__ __device__ constexpr double boys_tmax(int L) {
 template <int L>
 __device__ __forceinline__ void boys(double T, const double* __restrict__ table, double (&F)[L + 1]) {
     if (T < boys_tmax(L)) {
+#ifdef QCF_FAKE_BOYS      // timing experiment only (wrong results): every lane reads table row 0
+        const int g = 0;
+#else
         const int g = (int)(T * BOYS_PER_UNIT + 0.5);
+#endif
         const double d = (double)g * (1.0 / BOYS_PER_UNIT) - T;
         const double* r = table + ((size_t)L * BOYS_NGRID + g) * BOYS_ROW;
         double f = __ldg(r + 6);
@@ -525,6 +529,11 @@ struct KAcc {
     static constexpr int SIZE = (NA + NB) * (NC + ND);
 };
 
+#ifdef QCF_FAKE_GATHER     // timing experiment only (wrong results): every density gather reads element 0
+#define QCF_GIDX(x) ((size_t)0 * (x))
+#else
+#define QCF_GIDX(x) (x)
+#endif
 template <int LA, int LB, int LC, int LD, int NK>
 __device__ __forceinline__ void digest_slab_impl(const double* __restrict__ I, double* __restrict__ jab,
                                                  const double* __restrict__ pab, const BuildArgs& a, const AccMode fx, int fa, int fb,
@@ -535,7 +544,7 @@ __device__ __forceinline__ void digest_slab_impl(const double* __restrict__ I, d
     const int ICD = IC * ND + ID;
     const int N = a.N;
     {
-        const double pcd = __ldg(a.Pj + (size_t)(fc + IC) * N + fd + ID);
+        const double pcd = __ldg(a.Pj + QCF_GIDX((size_t)(fc + IC) * N + fd + ID));
         double s = 0.0;
 #pragma unroll
         for (int iab = 0; iab < NAB; ++iab) {
@@ -552,13 +561,13 @@ __device__ __forceinline__ void digest_slab_impl(const double* __restrict__ I, d
         double pbd[NB], pbc[NB], pad[NA], pac[NA];
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            pbd[i] = __ldg(Pk + (size_t)(fb + i) * N + fd + ID);
-            pbc[i] = __ldg(Pk + (size_t)(fb + i) * N + fc + IC);
+            pbd[i] = __ldg(Pk + QCF_GIDX((size_t)(fb + i) * N + fd + ID));
+            pbc[i] = __ldg(Pk + QCF_GIDX((size_t)(fb + i) * N + fc + IC));
         }
 #pragma unroll
         for (int i = 0; i < NA; ++i) {
-            pad[i] = __ldg(Pk + (size_t)(fa + i) * N + fd + ID);
-            pac[i] = __ldg(Pk + (size_t)(fa + i) * N + fc + IC);
+            pad[i] = __ldg(Pk + QCF_GIDX((size_t)(fa + i) * N + fd + ID));
+            pac[i] = __ldg(Pk + QCF_GIDX((size_t)(fa + i) * N + fc + IC));
         }
         double kbc_s[NB], kbd_s[NB];
 #pragma unroll

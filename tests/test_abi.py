@@ -169,3 +169,19 @@ def test_native_loader_errors_are_reported(tmp_path):
     heavy.write_text('[{"element": "92", "position": [0, 0, 0]}]')
     with pytest.raises(engine.FockError, match="no element"):
         engine.NativeSystem(DATA / "basis" / "STO-3G.json", heavy)
+
+
+def test_cli_occupations_and_parser():
+    """qchem_cli.py (stand-in for qchem-cli, main.rs:10-62): flags parse like the reference's; --charge and
+    --spin-multiplicity are honoured, multiplicity 0 keeps the reference semantics (uhf.rs:43-45)."""
+    from qchem_rs_b200 import cli
+    assert cli.occupations(16, 0, 0) == (8, 8)        # O2, reference semantics
+    assert cli.occupations(16, 0, 3) == (9, 7)        # triplet O2
+    assert cli.occupations(10, 1, 2) == (5, 4)        # water cation doublet
+    assert cli.occupations(10, -1, 2) == (6, 5)
+    with pytest.raises(SystemExit):
+        cli.occupations(10, 0, 2)                     # even electron count cannot be a doublet
+    args = cli.build_parser().parse_args(["uhf", "-b", "b.json", "-m", "m.json", "-c", "1", "-s", "2", "--max-iterations", "50"])
+    assert (args.command, args.charge, args.spin_multiplicity, args.max_iterations, args.epsilon) == ("uhf", 1, 2, 50, 1e-6)
+    args = cli.build_parser().parse_args(["rhf", "--basis-set", "b.json", "--molecule", "m.json"])
+    assert args.max_iterations == 100 and args.backend == "device" and args.gpus == 1

@@ -372,3 +372,41 @@ def test_cli_driver_runs_rhf_and_triplet_uhf(capsys):
     rc = cli.main(["uhf", "-b", str(DATA / "basis" / "6-31G.json"), "-m", str(DATA / "mol" / "oxygen.json"), "-s", "3",
                    "--max-iterations", "200", "--epsilon", "1e-4", "--backend", "host"])
     assert rc in (0, 1)      # the reference's DIIS(2,8) loop may stall for this state (see test_gpu_parity); it must not crash
+
+
+def test_production_kernels_reproduce_integrals_through_one_hot_densities():
+    """qcf_eri_quartet runs the diagnostic (local-memory) path for the dp / dd classes, so the quartet-level
+    tests never touched the PRODUCTION kernels of those classes.  Here the Fock-build kernels themselves (block and slab,
+    screening off) are probed integral by integral: with the one-hot density P = e_k e_l^T + e_l e_k^T,
+    J_ij = 2 (ij|kl) and K_ij = (ik|jl) + (il|jk) (halved on the diagonal k = l), compared with the oracle's N^4 tensor for
+    every (i, j) and a sample of (k, l) that covers every pair of shell types of the s/p/d test system, including
+    contracted d shells."""
+    from qchem_rs_b200.basis import MolecularSystem, Atom, Shell
+    rng = np.random.default_rng(3)
+    atoms = [Atom(1, rng.normal(size=3) * 1.2) for _ in range(3)]
+    system = MolecularSystem(atoms)
+    for ia in range(3):
+        for l, k in ((0, 2), (1, 2), (2, 2), (2, 1)):     # contracted s, p, d and an uncontracted d per centre
+            system.shells.append(Shell(l, rng.uniform(0.4, 2.5, size=k), rng.uniform(0.3, 1.0, size=k), "gto_cartesian"))
+            system.shell_atom.append(ia)
+    fb = system.flat()
+    n = fb.n_basis
+    eri = oracle_lib.eri_tensor(fb)
+    off = np.concatenate([[0], np.cumsum([(l + 1) * (l + 2) // 2 for l in fb.shell_l])])
+    picks = set()
+    ns = len(fb.shell_l)
+    for sa in range(ns):                 # one function pair per shell pair: every (l_k, l_l) combination on every centre pair
+        for sb in range(sa + 1):
+            k = int(rng.integers(off[sa], off[sa + 1])); l = int(rng.integers(off[sb], off[sb + 1]))
+            picks.add((max(k, l), min(k, l)))
+    worst_j = worst_k = 0.0
+    with engine.FockEngine(system, tau=engine.QCF_TAU_NONE) as eng:
+        for k, l in sorted(picks):
+            P = np.zeros((n, n))
+            P[k, l] = 1.0; P[l, k] = 1.0
+            (J,), (K,) = eng.jk([P])
+            w = 1.0 if k == l else 2.0
+            worst_j = max(worst_j, float(np.max(np.abs(J - w * eri[:, :, k, l]))))
+            kref = eri[:, k, :, l] + (eri[:, l, :, k] if k != l else 0.0)
+            worst_k = max(worst_k, float(np.max(np.abs(K - kref))))
+    assert worst_j < 1e-11 and worst_k < 1e-11, (worst_j, worst_k)
