@@ -821,22 +821,13 @@ int run_build_impl(qcf_ctx* ctx, int mode, const double* dPa, const double* dPb,
 #undef CKD
         return QCF_OK;
     };
-    // graphs already captured: the devices are enqueued from the pool's threads at once (a graph launch costs ~50 us of host
-    // time, so eight in a row would start the last device 0.35 ms late); first use and profile mode stay on this thread
-    bool parallel = nd > 1 && ctx->pool && ctx->pool->threads() > 1 && ctx->use_graph && !ctx->profile;
-    for (auto& dv : ctx->dev) parallel = parallel && dv.graph != nullptr;
-    if (parallel) {
-        std::vector<int> rcs(nd, 0);
-        std::vector<std::string> errs(nd);
-        const int T = ctx->pool->threads();
-        ctx->pool->run([&](int t) { for (int d = t; d < nd; d += T) rcs[d] = enqueue_one(d, errs[d]); });
-        for (int d = 0; d < nd; ++d) if (rcs[d]) { ctx->err = errs[d]; return rcs[d]; }
-    } else {
-        for (int d = 0; d < nd; ++d) {
-            std::string err;
-            int rc = enqueue_one(d, err);
-            if (rc) { ctx->err = err; return rc; }
-        }
+    // The devices are enqueued one after the other from the calling thread (~50 us of host time per graph launch).  Handing
+    // them to the copy pool's threads was measured and is SLOWER (0.69-0.81 ms instead of 0.36-0.40 ms of host time for eight
+    // devices: the launches serialise inside the driver and the hand-off adds wake-up latency), so it was not kept.
+    for (int d = 0; d < nd; ++d) {
+        std::string err;
+        int rc = enqueue_one(d, err);
+        if (rc) { ctx->err = err; return rc; }
     }
     graph_launches = graph_launches_atomic.load();
     PeerAcc acc{};
@@ -1117,7 +1108,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     CK(cudaSetDevice(device0));
     CK(cudaHostAlloc(&ctx->h_pin, 4 * nn * sizeof(double), cudaHostAllocPortable));
     {
-        int nthr = std::max(3, std::min(ngpus, 8) - 1);     // helper threads: staging copies, per-device graph launches
+        int nthr = 3;     // helper threads of the staging copies (plus the calling thread)
         if (const char* e = getenv("QCF_COPY_THREADS")) nthr = std::max(0, std::min(15, atoi(e) - 1));
         ctx->pool = new qcf_copy_pool(nthr);
     }
