@@ -164,6 +164,8 @@ def cpu_sample(fb, P, tau, budget_s, oracle_lib):
     t0 = time.perf_counter(); d.jk([P], stride=stride, offset=stride // 2); t1 = time.perf_counter()
     q = d.last_quartets
     return {"value": q / (t1 - t0), "unit": UNIT, "cores": ncores, "kind": "port",
+            "note": "oracle/qc_oracle.cpp: a plain -O2 restatement (long-double Boys series, no primitive screening) -- a checker "
+                    "first, a baseline second; the GPU/CPU ratio says nothing about kernel quality, the roofline fraction does",
             "sample": f"every {stride}-th bra shell pair of the same build ({q} quartets, {t1 - t0:.1f} s); "
                       f"extrapolated full build {(t1 - t0) * stride:.1f} s/iter",
             "seconds_per_iter_extrapolated": (t1 - t0) * stride}

@@ -607,8 +607,12 @@ int setup_device(qcf_ctx* ctx, qcf_device& dv, const std::vector<double>& boys_t
     CK(upload(&dv.fscale, ctx->fscale));
     CK(upload(&dv.shoff, ctx->sh_off));
     CK(cudaStreamCreateWithFlags(&dv.main, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));     // numerically lower = higher priority
     for (int s = 0; s < QCF_MAXSTREAM; ++s) {
-        CK(cudaStreamCreateWithFlags(&dv.streams[s], cudaStreamNonBlocking));
+        // QCF_PRIO: odd streams carry one kernel family at the other priority (see enqueue_device_work)
+        const int prio = (ctx->stream_prio != 0 && (s & 1)) ? prio_lo : prio_hi;
+        CK(cudaStreamCreateWithPriority(&dv.streams[s], cudaStreamNonBlocking, ctx->stream_prio != 0 ? prio : 0));
         CK(cudaEventCreateWithFlags(&dv.ev_join[s], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&dv.ev_fork, cudaEventDisableTiming));
@@ -728,7 +732,13 @@ int enqueue_device_work(qcf_ctx* ctx, qcf_device& dv, int mode, const double* pa
         BuildArgs al = a;
         al.counter = dv.counters + idx;
         al.bra_list = db.bra_list;
-        cudaStream_t st = dv.streams[ctx->profile ? 0 : (launched % nstr)];
+        int si = ctx->profile ? 0 : (launched % nstr);
+        if (ctx->stream_prio != 0 && !ctx->profile && nstr >= 2) {
+            // even streams: high priority, odd streams: low priority.  stream_prio 1: block kernels high, slab low; 2: reverse
+            const bool high = (ctx->stream_prio == 1) ? !slab : slab;
+            si = (si & ~1) | (high ? 0 : 1);
+        }
+        cudaStream_t st = dv.streams[si];
         if (ctx->profile) {
             while ((int)dv.prof_ev.size() < 2 * (idx + 1)) { cudaEvent_t e; CK(cudaEventCreate(&e)); dv.prof_ev.push_back(e); }
             CK(cudaEventRecord(dv.prof_ev[2 * idx], st));
@@ -1029,6 +1039,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     if (const char* e = getenv("QCF_PRIM_CUT")) ctx->prim_cut_factor = std::max(0.0, atof(e));
     if (const char* e = getenv("QCF_PAIR_CUT")) ctx->pair_cut_factor = std::max(0.0, atof(e));
     if (const char* e = getenv("QCF_ORDER")) ctx->launch_order = atoi(e);
+    if (const char* e = getenv("QCF_PRIO")) ctx->stream_prio = atoi(e);
     if (ctx->block < 32 || ctx->block > 128 || ctx->block % 32) return fail(QCF_ERR_ARG, "block_threads must be 32, 64, 96 or 128");
     ctx->natoms = b->n_atoms; ctx->nshell = b->n_shells;
     ctx->xyz.assign(b->xyz, b->xyz + 3 * b->n_atoms);

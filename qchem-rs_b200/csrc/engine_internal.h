@@ -79,6 +79,7 @@ struct qcf_ctx {
     double pair_cut_factor = 1e-2;    // shell pairs with Q Q_max below this fraction of tau are dropped at creation
     double prim_cut_factor = 1.0;     // primitive pairs with Q_k Q_max below this multiple of tau are dropped at creation
     bool screening = true, deterministic = false, use_graph = true, profile = false;
+    int stream_prio = 0;              // 0: one priority; 1: block kernels on high-priority streams, slab on low; 2: reverse (QCF_PRIO)
     int launch_order = 0;             // 0: longest-running threads first; 1: biggest launches first (QCF_ORDER)
     int ps_min_prim = 36;             // primitive quartets per shell quartet from which lanes share a quartet
     int world = 1;                    // total number of ranks in the bra split (processes x devices)
