@@ -525,6 +525,20 @@ int build_pairs(qcf_ctx* ctx) {
     return QCF_OK;
 }
 
+// Launch-shape defaults by the number of shell pairs one rank works on (measured, profiles/r2_ab_call10_rank_share_knobs.log,
+// r2_ab_call18_small_problems.log): a big share fills the GPU launch by launch -- 8 streams, ~296 CTAs per launch and 64 kets per
+// thread are best; the smaller the share, the more its 1/world-size (or small-molecule) grids depend on concurrency and on
+// fewer, longer CTAs: 16 streams / 148 CTAs, then 32 streams / 74 CTAs / 32 kets per thread.  Environment variables override.
+void tune_launch_shape(qcf_ctx* ctx) {
+    const size_t share = ctx->npairs / (size_t)std::max(ctx->world, 1);
+    int streams = 8, ctas = 296, kpt = ctx->world > 1 ? 32 : 64;
+    if (share < 16000) { streams = 32; ctas = 74; kpt = 32; }
+    else if (share < 40000) { streams = 16; ctas = 148; }
+    if (!getenv("QCF_STREAMS")) ctx->nstreams = streams;
+    if (!getenv("QCF_TARGET_CTAS")) ctx->target_ctas = ctas;
+    if (!getenv("QCF_KETS_PER_THREAD")) ctx->kets_per_thread = kpt;
+}
+
 // ---- launch plan and the cost-balanced bra split ------------------------------------------------------
 double per_quartet_cost(const HostGroup& bra, const HostGroup& ket) {
     return (double)bra.K * ket.K * model_flops_prim(bra.la, bra.lb, ket.la, ket.lb) + 400.0;
@@ -1023,12 +1037,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     if (ngpus > QCF_MAXDEV) return fail(QCF_ERR_ARG, "n_gpus too large");
     if (device0 < 0) return fail(QCF_ERR_ARG, "negative device ordinal");
     ctx->world = pworld * ngpus;
-    // measured on the N = 1007 build: 64 kets per thread is best when one GPU has the whole bra list, 32 for a
-    // rank's share of it (finer chunks keep the smaller grids balanced)
-    ctx->kets_per_thread = ctx->world > 1 ? 32 : 64;
-    // a rank's share of a multi-GPU run launches grids of 1/world the size: more streams keep more of them in flight and
-    // fewer, longer CTAs amortise the per-CTA prologue (measured on rank 0 of 8: 10.8 -> 9.9 ms; profiles/r2_ab_call10_rank_share_knobs.log)
-    if (ctx->world > 1) { ctx->nstreams = ctx->world >= 4 ? 32 : 16; ctx->target_ctas = ctx->world >= 4 ? 74 : 148; }
+    // (launch-shape defaults are chosen from the problem size after the pair lists exist, see tune_launch_shape below)
     if (const char* e = getenv("QCF_KETS_PER_THREAD")) ctx->kets_per_thread = std::max(1, atoi(e));
     if (const char* e = getenv("QCF_STREAMS")) ctx->nstreams = std::min(QCF_MAXSTREAM, std::max(1, atoi(e)));
     if (const char* e = getenv("QCF_SERIAL_CAP")) ctx->serial_cap = std::max(1.0, atof(e));
@@ -1098,6 +1107,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     CK(cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming));
     int rc = build_pairs(ctx);
     if (rc) return rc;
+    tune_launch_shape(ctx);
     make_plan(ctx);
     // peer access between all devices of the context (NVLink / NVSwitch): the finalize kernel reads every device's
     // accumulators directly

@@ -62,12 +62,16 @@ inline size_t block_smem_bytes(int braK, int nshell) {
 template <int NK, int PS>
 void launch_block(int nbra, int nket_max, int block, int kpt, cudaStream_t s, const PairGroup& bra, const PairGroup& ket, BuildArgs a, int same) {
     if constexpr (!USE_SLAB && PS <= MAX_PS) {
-        // candidates per CTA: kpt per thread, spread over PS lanes each; at least one full scan step per warp
+        // candidates per CTA: kpt per thread, spread over PS lanes each; at least one 32-candidate scan step per warp
         a.ket_chunk = block * kpt / PS;
-        const int min_chunk = block * BlockCfg<PS>::SW;
-        if (a.ket_chunk < min_chunk) a.ket_chunk = min_chunk;
+        if (a.ket_chunk < block) a.ket_chunk = block;
         const dim3 grid(nbra, (nket_max + a.ket_chunk - 1) / a.ket_chunk);
-        eri_jk_kernel<LA, LB, LC, LD, NK, PS><<<grid, block, block_smem_bytes(bra.K, a.nshell), s>>>(bra, ket, a, same);
+        const size_t smem = block_smem_bytes(bra.K, a.nshell);
+        // the wide-scan instantiation only when every warp gets a full wide step out of the chunk
+        if (BlockCfg<PS>::SW > 1 && a.ket_chunk >= block * BlockCfg<PS>::SW)
+            eri_jk_kernel<LA, LB, LC, LD, NK, PS, true><<<grid, block, smem, s>>>(bra, ket, a, same);
+        else
+            eri_jk_kernel<LA, LB, LC, LD, NK, PS, false><<<grid, block, smem, s>>>(bra, ket, a, same);
     }
 }
 
@@ -103,15 +107,17 @@ cudaError_t class_init(int max_bra_K, int nshell) {
         if (e == cudaSuccess) e = set_smem(eri_jk_slab_kernel<LA, LB, LC, LD, 2, SPT>, slab_smem_bytes<LA, LB, LC, LD, 2, SPT>(max_bra_K));
     } else {
         const size_t b = block_smem_bytes(max_bra_K, nshell);
-        e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 1>, b);
-        if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 2, 1>, b);
+        e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 1, true>, b);
+        if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 2, 1, true>, b);
+        if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 1, false>, b);
+        if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 2, 1, false>, b);
         if constexpr (MAX_PS >= 4) {
-            if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 4>, b);
-            if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 2, 4>, b);
+            if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 4, false>, b);
+            if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 2, 4, false>, b);
         }
         if constexpr (MAX_PS >= 8) {
-            if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 8>, b);
-            if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 2, 8>, b);
+            if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 8, false>, b);
+            if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 2, 8, false>, b);
         }
     }
     return e;

@@ -686,13 +686,16 @@ template <int PS> struct BlockCfg {
     static constexpr int SW = PS == 1 ? QCF_SCANW : 1;        // scan width: a PS > 1 warp consumes only 32/PS quartets per pass
     static constexpr int QLEN = 32 * (SW + 1);
 };
-template <int LA, int LB, int LC, int LD, int NK, int PS>
+// WIDE: scan steps of SW candidates per lane; chosen by the launcher when the chunk gives every warp a full wide step.
+// Short chunks (small molecules, a rank's share of few bras: kets per CTA are cut fine to fill the GPU) use the
+// instantiation that scans 32 candidates per step, so that no warp idles.
+template <int LA, int LB, int LC, int LD, int NK, int PS, bool WIDE>
 __global__ void __launch_bounds__(128)
 eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     using KA = KAcc<LA, LB, LC, LD>;
     constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
     constexpr int NAB = NA * NB, NCD = NC * ND, NI = NAB * NCD;
-    constexpr int SW = BlockCfg<PS>::SW, QLEN = BlockCfg<PS>::QLEN, QPW = 32 / PS;
+    constexpr int SW = WIDE ? BlockCfg<PS>::SW : 1, QLEN = BlockCfg<PS>::QLEN, QPW = 32 / PS;
     const int ib_ = a.bra_list ? __ldg(a.bra_list + blockIdx.x) : (int)blockIdx.x;
     const double qab = __ldg(bra.Q + ib_);
     const int ket0 = blockIdx.y * a.ket_chunk;

@@ -336,11 +336,14 @@ eri_jk_slab_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     const float* const dsh_b = a.Dsh + (size_t)sb * a.nshell;
     int* const queue = ket_queue[ksub];
     int qn = 0;
-    int scan = ket0 + ksub * (32 * SW);
+    const bool wide = a.ket_chunk >= 32 * NSUB * SW;      // see eri_jk_kernel: short chunks scan 32 candidates per step
+    const int sw_eff = wide ? SW : 1;
+    int scan = ket0 + ksub * (32 * sw_eff);
     while (true) {
         while (qn < 32 && scan < nket) {
-            qn = scan_kets<SW>(ket, a.tau, scan, nket, qab, dab, dsh_a, dsh_b, queue, qn, lane);
-            scan += 32 * NSUB * SW;
+            qn = wide ? scan_kets<SW>(ket, a.tau, scan, nket, qab, dab, dsh_a, dsh_b, queue, qn, lane)
+                      : scan_kets<1>(ket, a.tau, scan, nket, qab, dab, dsh_a, dsh_b, queue, qn, lane);
+            scan += 32 * NSUB * sw_eff;
         }
         __syncwarp();
         const int nrun = qn < 32 ? qn : 32;

@@ -18,6 +18,8 @@ pkg = qcpkg.load()
 
 
 def density(system, eng, n, iters=6):
+    if os.environ.get("AB_MOL"):
+        n = -1
     f = ROOT / "tests" / "golden" / f"waters{n}_scf{iters}_density_factor.npz"
     if f.exists():
         L = np.load(f)["L"]
@@ -44,7 +46,10 @@ def main():
     topn = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     tag = os.environ.get("AB_TAG", "")
     bs = pkg.BasisSet.load(ROOT / "data" / "basis" / "6-31G_st.json")
-    system = pkg.MolecularSystem.from_atoms(pkg.molecules.water_cluster(n), bs)
+    if os.environ.get("AB_MOL"):            # a molecule file of data/mol instead of a water cluster (n is ignored)
+        system = pkg.MolecularSystem.load(ROOT / "data" / "mol" / (os.environ["AB_MOL"] + ".json"), bs)
+    else:
+        system = pkg.MolecularSystem.from_atoms(pkg.molecules.water_cluster(n), bs)
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
     ngpus = int(os.environ.get("AB_NGPUS", "1"))
     rank, world = int(os.environ.get("AB_RANK", "0")), int(os.environ.get("AB_WORLD", "1"))   # one rank's share of a multi-process run
