@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--deterministic", action="store_true", help="time the fixed-point (bitwise reproducible) mode")
     ap.add_argument("--scf", action="store_true", help="also time a whole device-resident SCF (reported in config.scf)")
+    ap.add_argument("--scf-epsilon", type=float, default=1e-6, help="convergence threshold of the --scf runs (density rms, rhf.rs:87-91)")
+    ap.add_argument("--scf-full-every", type=int, default=8, help="full rebuild period of the incremental --scf run")
     return ap.parse_args()
 
 
@@ -365,11 +367,11 @@ def run_b200(args):
 
     scf = None
     if args.scf and rank == 0 and world == 1:
-        cfg = pkg.hf.HartreeFockConfig(60, 1e-6)
+        cfg = pkg.hf.HartreeFockConfig(100, args.scf_epsilon)
         t0 = time.perf_counter(); out_dev = pkg.hf.restricted_hartree_fock_device(system, cfg, ints, eng); t1 = time.perf_counter()
-        t2 = time.perf_counter(); out_inc = pkg.hf.restricted_hartree_fock_device(system, cfg, ints, eng, full_rebuild_every=8); t3 = time.perf_counter()
-        scf = {"epsilon": 1e-6}
-        for name, o, dt in (("full_builds", out_dev, t1 - t0), ("incremental_every_8", out_inc, t3 - t2)):
+        t2 = time.perf_counter(); out_inc = pkg.hf.restricted_hartree_fock_device(system, cfg, ints, eng, full_rebuild_every=args.scf_full_every); t3 = time.perf_counter()
+        scf = {"epsilon": args.scf_epsilon}
+        for name, o, dt in (("full_builds", out_dev, t1 - t0), (f"incremental_every_{args.scf_full_every}", out_inc, t3 - t2)):
             if o is not None:
                 scf[name] = {"iterations": o.iterations, "wall_s": dt, "init_s": o.init_s,
                              "steps_wall_s": sum(s["wall_ms"] for s in o.steps) * 1e-3, "e_total": o.total_energy(),

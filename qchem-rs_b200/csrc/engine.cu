@@ -738,12 +738,7 @@ int enqueue_device_work(qcf_ctx* ctx, qcf_device& dv, int mode, const double* pa
         if (db.nbra <= 0) continue;
         const int nket_max = dk.pg.npair;
         const bool slab = bra.la == 2 && bra.lb >= 1;
-        // exchange rows in shared memory: low-contraction block-kernel launches, where the FP64 atomics are the bottleneck
-        const size_t krow_bytes = (size_t)(ncart(bra.la) + ncart(bra.lb)) * N * sizeof(double) + (size_t)bra.K * 72 + 8 * (size_t)ns;
-        const bool krows = !slab && nk == 1 && pl.ps == 1 && !ctx->deterministic && bra.K * ket.K <= ctx->krows_max_prim &&
-                           krow_bytes <= ctx->krows_smem;
-        const int block = krows ? ctx->krows_block : ctx->block;
-        const int cta_threads = slab ? 128 : block;
+        const int cta_threads = slab ? 128 : ctx->block;
         const long long want_chunks = (ctx->target_ctas + db.nbra - 1) / db.nbra;
         int kpt = (int)(nket_max / (want_chunks * cta_threads));
         kpt = std::min(kpt, (int)(ctx->serial_cap / pl.serial));
@@ -751,7 +746,6 @@ int enqueue_device_work(qcf_ctx* ctx, qcf_device& dv, int mode, const double* pa
         BuildArgs al = a;
         al.counter = dv.counters + idx;
         al.bra_list = db.bra_list;
-        al.krows = krows ? 1 : 0;
         int si = ctx->profile ? 0 : (launched % nstr);
         if (ctx->stream_prio != 0 && !ctx->profile && nstr >= 2) {
             // even streams: high priority, odd streams: low priority.  stream_prio 1: block kernels high, slab low; 2: reverse
@@ -763,7 +757,7 @@ int enqueue_device_work(qcf_ctx* ctx, qcf_device& dv, int mode, const double* pa
             while ((int)dv.prof_ev.size() < 2 * (idx + 1)) { cudaEvent_t e; CK(cudaEventCreate(&e)); dv.prof_ev.push_back(e); }
             CK(cudaEventRecord(dv.prof_ev[2 * idx], st));
         }
-        class_table(bra.cls, ket.cls)->jk(nk, pl.ps, db.nbra, nket_max, block, kpt, st, db.pg, dk.pg, al, pl.gi == pl.gj ? 1 : 0);
+        class_table(bra.cls, ket.cls)->jk(nk, pl.ps, db.nbra, nket_max, ctx->block, kpt, st, db.pg, dk.pg, al, pl.gi == pl.gj ? 1 : 0);
         if (ctx->profile) CK(cudaEventRecord(dv.prof_ev[2 * idx + 1], st));
         ++launched;
     }
@@ -1050,9 +1044,6 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     if (const char* e = getenv("QCF_TARGET_CTAS")) ctx->target_ctas = std::max(1, atoi(e));
     if (const char* e = getenv("QCF_PS_MIN")) ctx->ps_min_prim = std::max(1, atoi(e));
     if (const char* e = getenv("QCF_BLOCK")) ctx->block = atoi(e);
-    if (const char* e = getenv("QCF_KROWS_MAX_PRIM")) ctx->krows_max_prim = std::max(0, atoi(e));
-    if (const char* e = getenv("QCF_KROWS_BLOCK")) ctx->krows_block = atoi(e);
-    if (const char* e = getenv("QCF_KROWS_SMEM")) ctx->krows_smem = (size_t)std::min(100 * 1024, std::max(0, atoi(e)));
     if (const char* e = getenv("QCF_RED_EPS_FACTOR")) ctx->red_eps_factor = std::max(0.0, atof(e));
     if (const char* e = getenv("QCF_PRIM_CUT")) ctx->prim_cut_factor = std::max(0.0, atof(e));
     if (const char* e = getenv("QCF_PAIR_CUT")) ctx->pair_cut_factor = std::max(0.0, atof(e));

@@ -81,10 +81,6 @@ struct qcf_ctx {
     bool screening = true, deterministic = false, use_graph = true, profile = false;
     int stream_prio = 0;              // 0: one priority; 1: block kernels on high-priority streams, slab on low; 2: reverse (QCF_PRIO)
     int launch_order = 0;             // 0: longest-running threads first; 1: biggest launches first (QCF_ORDER)
-    // shared-memory exchange rows (KROWS instantiation of the block kernel, RHF / J,K builds in FP64-atomic mode): used for
-    // launches with at most krows_max_prim primitive quartets per shell quartet whose rows fit krows_smem bytes
-    int krows_max_prim = 0, krows_block = 128;
-    size_t krows_smem = 64 * 1024;
     int ps_min_prim = 36;             // primitive quartets per shell quartet from which lanes share a quartet
     int world = 1;                    // total number of ranks in the bra split (processes x devices)
     // basis (host copies)

@@ -59,11 +59,6 @@ inline size_t block_smem_bytes(int braK, int nshell) {
     return (size_t)braK * BRA_S * sizeof(double) + 2 * (size_t)nshell * sizeof(float);
 }
 
-// shared-memory exchange rows of the KROWS instantiation: (NA + NB) rows of N doubles; at most KROW_SMEM_MAX bytes of
-// dynamic shared memory per CTA in total (two CTAs per SM)
-constexpr size_t KROW_SMEM_MAX = 100 * 1024;
-inline size_t krow_smem_bytes(int N) { return (size_t)(ncart(LA) + ncart(LB)) * N * sizeof(double); }
-
 template <int NK, int PS>
 void launch_block(int nbra, int nket_max, int block, int kpt, cudaStream_t s, const PairGroup& bra, const PairGroup& ket, BuildArgs a, int same) {
     if constexpr (!USE_SLAB && PS <= MAX_PS) {
@@ -72,18 +67,8 @@ void launch_block(int nbra, int nket_max, int block, int kpt, cudaStream_t s, co
         if (a.ket_chunk < block) a.ket_chunk = block;
         const dim3 grid(nbra, (nket_max + a.ket_chunk - 1) / a.ket_chunk);
         const size_t smem = block_smem_bytes(bra.K, a.nshell);
-        const bool wide = BlockCfg<PS>::SW > 1 && a.ket_chunk >= block * BlockCfg<PS>::SW;
-        if constexpr (NK == 1 && PS == 1) {
-            // exchange rows of the bra pair in shared memory (the engine asks for it per launch and has checked the size)
-            const size_t smem_k = smem + krow_smem_bytes(a.N);
-            if (a.krows && smem_k <= KROW_SMEM_MAX) {
-                if (wide) eri_jk_kernel<LA, LB, LC, LD, 1, 1, true, true><<<grid, block, smem_k, s>>>(bra, ket, a, same);
-                else eri_jk_kernel<LA, LB, LC, LD, 1, 1, false, true><<<grid, block, smem_k, s>>>(bra, ket, a, same);
-                return;
-            }
-        }
         // the wide-scan instantiation only when every warp gets a full wide step out of the chunk
-        if (wide)
+        if (BlockCfg<PS>::SW > 1 && a.ket_chunk >= block * BlockCfg<PS>::SW)
             eri_jk_kernel<LA, LB, LC, LD, NK, PS, true><<<grid, block, smem, s>>>(bra, ket, a, same);
         else
             eri_jk_kernel<LA, LB, LC, LD, NK, PS, false><<<grid, block, smem, s>>>(bra, ket, a, same);
@@ -126,8 +111,6 @@ cudaError_t class_init(int max_bra_K, int nshell) {
         if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 2, 1, true>, b);
         if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 1, false>, b);
         if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 2, 1, false>, b);
-        if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 1, true, true>, KROW_SMEM_MAX);
-        if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 1, false, true>, KROW_SMEM_MAX);
         if constexpr (MAX_PS >= 4) {
             if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 1, 4, false>, b);
             if (e == cudaSuccess) e = set_smem(eri_jk_kernel<LA, LB, LC, LD, 2, 4, false>, b);

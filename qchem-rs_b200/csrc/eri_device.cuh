@@ -81,7 +81,6 @@ struct BuildArgs {
     const int* bra_list;      // this rank's share of the bra list (cost-balanced split); null: every bra pair
     double red_eps;           // scatter contributions below this magnitude are skipped (0.1 tau; 0 without screening)
     int ket_chunk;            // kets per CTA (grid.y strides over the ket list)
-    int krows;                // host-side launch hint: use the instantiation that sums the exchange rows in shared memory
 };
 
 // ---- fast reciprocal square root / reciprocal (positive, normal arguments) --------------------------
@@ -513,16 +512,6 @@ __device__ __forceinline__ void red_add(double* addr, double v, const AccMode m)
     }
 }
 
-// Exchange rows of the bra pair summed in shared memory (KROWS instantiation of the block kernel): every exchange
-// contribution of a quartet lands in row a or row b of AK, and the bra pair is fixed per CTA, so the CTA keeps those
-// NA + NB rows (N columns each) in shared memory, adds to them with shared-memory atomics (a compare-and-swap loop in
-// SASS, ATOMS.CAST.SPIN.64, but off the global LSU path) and sends every non-zero element to memory once at the end.
-__device__ __forceinline__ void smem_add(double* addr, double v, const AccMode m) {
-    if (!(fabs(v) >= m.eps)) return;
-    const unsigned int sa = (unsigned int)__cvta_generic_to_shared(addr);
-    asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(sa), "d"(v) : "memory");
-}
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -700,12 +689,9 @@ template <int PS> struct BlockCfg {
 // WIDE: scan steps of SW candidates per lane; chosen by the launcher when the chunk gives every warp a full wide step.
 // Short chunks (small molecules, a rank's share of few bras: kets per CTA are cut fine to fill the GPU) use the
 // instantiation that scans 32 candidates per step, so that no warp idles.
-// KROWS: the exchange rows of the bra pair are accumulated in shared memory and flushed once per CTA (see smem_add;
-// NK = 1, PS = 1, FP64-atomic mode only -- the launcher falls back to the plain instantiation otherwise).
-template <int LA, int LB, int LC, int LD, int NK, int PS, bool WIDE, bool KROWS = false>
+template <int LA, int LB, int LC, int LD, int NK, int PS, bool WIDE>
 __global__ void __launch_bounds__(128)
 eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
-    static_assert(!KROWS || (NK == 1 && PS == 1), "shared-memory exchange rows: single exchange density, one lane per quartet");
     using KA = KAcc<LA, LB, LC, LD>;
     constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
     constexpr int NAB = NA * NB, NCD = NC * ND, NI = NAB * NCD;
@@ -736,9 +722,6 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
             dsh_a[t] = __ldg(a.Dsh + (size_t)sa * a.nshell + t);
             dsh_b[t] = __ldg(a.Dsh + (size_t)sb * a.nshell + t);
         }
-    double* const krow = reinterpret_cast<double*>(dsh_b + a.nshell);                // [NA + NB][N]  (KROWS only)
-    if constexpr (KROWS)
-        for (int t = threadIdx.x; t < (NA + NB) * N; t += blockDim.x) krow[t] = 0.0;
     double ABx = 0, ABy = 0, ABz = 0;
     if constexpr (LB > 0) {
         ABx = __ldg(bra.AB + ib_); ABy = __ldg(bra.AB + bra.npair + ib_); ABz = __ldg(bra.AB + 2 * (size_t)bra.npair + ib_);
@@ -787,22 +770,6 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
 #pragma unroll
         for (int i = 0; i < NK * KA::SIZE; ++i) kacc[i] = 0.0;
         digest_all<LA, LB, LC, LD, NK>(I, jab, pab, a, fx, fa, fb, fc, fd, kacc);
-        if constexpr (KROWS) {
-#pragma unroll
-            for (int i = 0; i < NA; ++i) {
-#pragma unroll
-                for (int j = 0; j < NC; ++j) smem_add(krow + i * N + fc + j, kacc[KA::OFF_AC + i * NC + j], fx);
-#pragma unroll
-                for (int j = 0; j < ND; ++j) smem_add(krow + i * N + fd + j, kacc[KA::OFF_AD + i * ND + j], fx);
-            }
-#pragma unroll
-            for (int i = 0; i < NB; ++i) {
-#pragma unroll
-                for (int j = 0; j < NC; ++j) smem_add(krow + (NA + i) * N + fc + j, kacc[KA::OFF_BC + i * NC + j], fx);
-#pragma unroll
-                for (int j = 0; j < ND; ++j) smem_add(krow + (NA + i) * N + fd + j, kacc[KA::OFF_BD + i * ND + j], fx);
-            }
-        } else {
 #pragma unroll
         for (int kk = 0; kk < NK; ++kk) {
             double* __restrict__ AK = kk == 0 ? a.AK0 : a.AK1;
@@ -822,7 +789,6 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
                 for (int j = 0; j < ND; ++j) red_add(AK + (size_t)(fb + i) * N + fd + j, acc[KA::OFF_BD + i * ND + j], fx);
             }
         }
-        }   // !KROWS
         }   // sub == 0
         }   // slot < nrun
         qn -= nrun;
@@ -840,18 +806,6 @@ eri_jk_kernel(PairGroup bra, PairGroup ket, BuildArgs a, int same_group) {
     __shared__ unsigned int nqs[4];
     if (lane == 0) nqs[warp] = nq;
     __syncthreads();
-    if constexpr (KROWS) {
-        // every non-zero element of the CTA's exchange rows goes to memory once
-#pragma unroll
-        for (int r = 0; r < NA + NB; ++r) {
-            double* __restrict__ dst = a.AK0 + (size_t)(r < NA ? fa + r : fb + r - NA) * N;
-            const double* __restrict__ src = krow + r * N;
-            for (int c = threadIdx.x; c < N; c += blockDim.x) {
-                const double v = src[c];
-                if (v != 0.0) asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + c), "d"(v) : "memory");
-            }
-        }
-    }
     const int nwarp = (blockDim.x + 31) >> 5;
     for (int i = threadIdx.x; i < NAB; i += blockDim.x) {
         double s = 0.0;

@@ -17,7 +17,9 @@
 #include <cusolverDn.h>
 
 #include <chrono>
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <deque>
 
 namespace {
@@ -37,6 +39,7 @@ struct Diis {
 struct qcf_scf {
     int N = 0, nspin = 1, nocc[2] = {0, 0}, iteration = 0, full_every = 0, since_full = 0;
     double last_rms = 1.0;           // density rms of the previous step: difference-density builds pay off only once it is small
+    double inc_rms = 1e-4;           // ... i.e. below this rms (QCF_INC_RMS)
     double factor = 2.0;
     cublasHandle_t blas = nullptr;
     cusolverDnHandle_t sol = nullptr;
@@ -271,6 +274,7 @@ int qcf_scf_init(qcf_ctx* ctx, const double* S, const double* H, int unrestricte
     s->N = N; s->nspin = unrestricted ? 2 : 1; s->nocc[0] = n_alpha; s->nocc[1] = unrestricted ? n_beta : n_alpha;
     s->factor = unrestricted ? 1.0 : 2.0;
     s->full_every = full_rebuild_every;
+    if (const char* e = getenv("QCF_INC_RMS")) s->inc_rms = std::max(0.0, atof(e));
     const size_t nn = (size_t)N * N;
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&s->e0)); CK(cudaEventCreate(&s->e1)); CK(cudaEventCreate(&s->e2));
@@ -335,7 +339,7 @@ int qcf_scf_step(qcf_ctx* ctx, double epsilon, qcf_scf_info* out) {
     // difference-density builds once the density moves little (their screening runs on |P - P_prev|, at tau / 8): while the
     // SCF is far from convergence a full build is cheaper; a full rebuild every `full_every` steps bounds the accumulated error
     const bool inc = s->full_every > 0;
-    const bool reset = inc && (s->since_full == 0 || s->last_rms > 1e-4);
+    const bool reset = inc && (s->since_full == 0 || s->last_rms > s->inc_rms);
     int rc = qcf_internal::run_build_scf(ctx, s->nspin == 2 ? 1 : 0, s->P[0], s->nspin == 2 ? s->P[1] : nullptr, s->G[0],
                                          s->nspin == 2 ? s->G[1] : nullptr, s->stream, inc, reset);
     if (rc) return rc;

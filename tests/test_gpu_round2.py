@@ -410,39 +410,3 @@ def test_production_kernels_reproduce_integrals_through_one_hot_densities():
             kref = eri[:, k, :, l] + (eri[:, l, :, k] if k != l else 0.0)
             worst_k = max(worst_k, float(np.max(np.abs(K - kref))))
     assert worst_j < 1e-11 and worst_k < 1e-11, (worst_j, worst_k)
-
-
-@pytest.mark.parametrize("block", ["128", "64"])
-def test_shared_memory_exchange_rows_match_global_atomics(block):
-    """The KROWS instantiation of the block kernel (exchange rows of the bra pair summed in shared memory, flushed once
-    per CTA; QCF_KROWS_MAX_PRIM selects the launches) against the plain instantiation and the dense oracle, with and
-    without screening, on a system with s, p and d shells; RHF and J/K entry points."""
-    system = water_cluster(3)
-    fb = system.flat()
-    n = fb.n_basis
-    P = random_symmetric_density(n, 41)
-    ref = oracle_lib.DenseFock(fb).rhf(P)
-    out = {}
-    for tag, env in (("plain", {"QCF_KROWS_MAX_PRIM": "0"}), ("krows", {"QCF_KROWS_MAX_PRIM": "1000000", "QCF_KROWS_BLOCK": block})):
-        saved = {key: os.environ.get(key) for key in env}
-        os.environ.update(env)
-        try:
-            for tau in (1e-12, engine.QCF_TAU_NONE):
-                with engine.FockEngine(system, tau=tau) as eng:
-                    g = eng.rhf(P)
-                    (j,), (k,) = eng.jk([P])
-                    out[tag, tau] = (g, j, k, eng.stats()["quartets"])
-        finally:
-            for key, val in saved.items():
-                if val is None:
-                    del os.environ[key]
-                else:
-                    os.environ[key] = val
-    for tau in (1e-12, engine.QCF_TAU_NONE):
-        g0, j0, k0, q0 = out["plain", tau]
-        g1, j1, k1, q1 = out["krows", tau]
-        assert q0 == q1
-        assert np.array_equal(g1, g1.T) and np.array_equal(k1, k1.T)
-        assert np.max(np.abs(g1 - g0)) < 1e-11 and np.max(np.abs(j1 - j0)) < 1e-11 and np.max(np.abs(k1 - k0)) < 1e-11
-        assert np.max(np.abs(g1 - ref)) < F_TOL
-        assert np.max(np.abs(j1 - 0.5 * k1 - ref)) < F_TOL
