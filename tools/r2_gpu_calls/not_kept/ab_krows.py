@@ -1,7 +1,10 @@
 """A/B of the shared-memory exchange rows (KROWS instantiation of the block kernel) in ONE process: for every
 configuration (a set of QCF_* environment knobs read by qcf_create) the whole-build device time at N = 1007, the
 difference of G to the first configuration's G, and optionally the serialised per-class times (QCF_PROFILE=1).
-  python tools/ab_krows.py [n_waters=53] [reps=5]"""
+  python tools/ab_krows.py [n_waters=53] [reps=5]
+
+Record of GPU call 19 (profiles/r2_ab_call19_smem_exchange_rows.log).  The QCF_KROWS_* knobs exist only in the library
+of commit ccb1038; the variant was measured slower and removed (profiles/README.md, "Experiments that were not kept")."""
 import collections
 import os
 import sys
@@ -9,7 +12,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[3]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tools"))
 import qcpkg  # noqa: E402
