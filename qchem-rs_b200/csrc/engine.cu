@@ -896,11 +896,17 @@ int host_build(qcf_ctx* ctx, int mode, const double* Pa, const double* Pb, doubl
         full_rebuild = reset || ctx->incremental_builds == 0;
     }
     CK(cudaEventRecord(ctx->ev_h0, ms));
-    ctx->pool->copy(ctx->h_pin, Pa, nn * sizeof(double));
-    CK(cudaMemcpyAsync(d0.Pin[0], ctx->h_pin, nn * sizeof(double), cudaMemcpyHostToDevice, ms));
-    if (Pb) {
-        ctx->pool->copy(ctx->h_pin + nn, Pb, nn * sizeof(double));
-        CK(cudaMemcpyAsync(d0.Pin[1], ctx->h_pin + nn, nn * sizeof(double), cudaMemcpyHostToDevice, ms));
+    // Staging through pinned memory in pieces: the DMA of one piece runs while the host threads copy the next one
+    // (matrices below 2 MB go in one piece).
+    const int nchunk = nn * sizeof(double) >= (size_t(2) << 20) ? QCF_STAGE_CHUNKS : 1;
+    auto piece = [&](int c) { return nn * (size_t)c / nchunk; };
+    for (int k = 0; k < (Pb ? 2 : 1); ++k) {
+        const double* src = k == 0 ? Pa : Pb;
+        for (int c = 0; c < nchunk; ++c) {
+            const size_t lo = piece(c), len = piece(c + 1) - lo;
+            ctx->pool->copy(ctx->h_pin + k * nn + lo, src + lo, len * sizeof(double));
+            CK(cudaMemcpyAsync(d0.Pin[k] + lo, ctx->h_pin + k * nn + lo, len * sizeof(double), cudaMemcpyHostToDevice, ms));
+        }
     }
     double* g0 = incremental ? d0.Gprev[0] : d0.G[0];
     double* g1 = incremental ? d0.Gprev[1] : d0.G[1];
@@ -908,12 +914,22 @@ int host_build(qcf_ctx* ctx, int mode, const double* Pa, const double* Pb, doubl
                          : run_build_impl(ctx, mode, d0.Pin[0], Pb ? d0.Pin[1] : nullptr, g0, g1, ms, false);
     if (rc) return rc;
     if (incremental) ++ctx->incremental_builds;
-    CK(cudaMemcpyAsync(ctx->h_pin + 2 * nn, g0, nn * sizeof(double), cudaMemcpyDeviceToHost, ms));
-    if (G1) CK(cudaMemcpyAsync(ctx->h_pin + 3 * nn, g1, nn * sizeof(double), cudaMemcpyDeviceToHost, ms));
+    // ... and back the same way: every piece of G is copied out of the pinned buffer while the next one is in flight
+    const int nout = G1 ? 2 : 1;
+    for (int k = 0; k < nout; ++k)
+        for (int c = 0; c < nchunk; ++c) {
+            const size_t lo = piece(c), len = piece(c + 1) - lo;
+            CK(cudaMemcpyAsync(ctx->h_pin + (2 + k) * nn + lo, (k == 0 ? g0 : g1) + lo, len * sizeof(double), cudaMemcpyDeviceToHost, ms));
+            CK(cudaEventRecord(ctx->ev_out[k * QCF_STAGE_CHUNKS + c], ms));
+        }
     CK(cudaEventRecord(ctx->ev_h1, ms));
+    for (int k = 0; k < nout; ++k)
+        for (int c = 0; c < nchunk; ++c) {
+            const size_t lo = piece(c), len = piece(c + 1) - lo;
+            CK(cudaEventSynchronize(ctx->ev_out[k * QCF_STAGE_CHUNKS + c]));
+            ctx->pool->copy((k == 0 ? G0 : G1) + lo, ctx->h_pin + (2 + k) * nn + lo, len * sizeof(double));
+        }
     CK(cudaStreamSynchronize(ms));
-    ctx->pool->copy(G0, ctx->h_pin + 2 * nn, nn * sizeof(double));
-    if (G1) ctx->pool->copy(G1, ctx->h_pin + 3 * nn, nn * sizeof(double));
     float t = 0;
     CK(cudaEventElapsedTime(&t, ctx->ev_h0, ctx->ev_h1));
     ctx->stats.total_ms = t;
@@ -1105,6 +1121,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     CK(cudaEventCreate(&ctx->ev_t0)); CK(cudaEventCreate(&ctx->ev_t1));
     CK(cudaEventCreate(&ctx->ev_h0)); CK(cudaEventCreate(&ctx->ev_h1));
     CK(cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming));
+    for (cudaEvent_t& e : ctx->ev_out) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     int rc = build_pairs(ctx);
     if (rc) return rc;
     tune_launch_shape(ctx);
@@ -1388,6 +1405,7 @@ void qcf_destroy(qcf_ctx* ctx) {
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     delete ctx->pool;
     for (cudaEvent_t e : {ctx->ev_t0, ctx->ev_t1, ctx->ev_h0, ctx->ev_h1, ctx->ev_in}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_out) if (e) cudaEventDestroy(e);
     delete ctx;
 }
 

@@ -37,6 +37,7 @@ struct PlannedLaunch {
     double serial, cost;
 };
 
+constexpr int QCF_STAGE_CHUNKS = 4;       // host-buffer calls move P and G in this many pipelined pieces
 constexpr int QCF_MAXSTREAM = 32;
 constexpr int QCF_MAXDEV = 16;
 
@@ -100,6 +101,7 @@ struct qcf_ctx {
     double* h_pin = nullptr;          // pinned staging, 4*N*N
     struct qcf_copy_pool* pool = nullptr;   // helper threads of the host staging copies
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_h0 = nullptr, ev_h1 = nullptr, ev_in = nullptr;
+    cudaEvent_t ev_out[2 * QCF_STAGE_CHUNKS] = {};   // one per D2H chunk of the host-buffer calls (pipelined staging)
     // stats of the last build
     struct LaunchRec { int bra, ket; float ms = 0; };
     std::vector<LaunchRec> launches;
