@@ -534,6 +534,10 @@ void tune_launch_shape(qcf_ctx* ctx) {
     int streams = 8, ctas = 296, kpt = ctx->world > 1 ? 32 : 64;
     if (share < 16000) { streams = 32; ctas = 74; kpt = 32; }
     else if (share < 40000) { streams = 16; ctas = 148; }
+    // Bra split: per launch from four ranks on (a launch is shared by as many ranks as get at least 148 bra pairs each; measured
+    // for the eight ranks of an N = 1007 build on one GPU, profiles/r2_ab_call24_per_launch_split.log: slowest rank 9.84 ->
+    // 9.39 ms, every rank faster), per group below
+    if (!getenv("QCF_SPLIT_MIN_BRAS")) ctx->split_min_bras = ctx->world >= 4 ? 148 : 0;
     if (!getenv("QCF_STREAMS")) ctx->nstreams = streams;
     if (!getenv("QCF_TARGET_CTAS")) ctx->target_ctas = ctas;
     if (!getenv("QCF_KETS_PER_THREAD")) ctx->kets_per_thread = kpt;
@@ -544,9 +548,69 @@ double per_quartet_cost(const HostGroup& bra, const HostGroup& ket) {
     return (double)bra.K * ket.K * model_flops_prim(bra.la, bra.lb, ket.la, ket.lb) + 400.0;
 }
 
+// modelled cost of bra pair i of group `bra` against ket group `ket` (length of its Schwarz prefix x cost per quartet)
+double bra_item_cost(const qcf_ctx* ctx, const HostGroup& bra, const HostGroup& ket, int i, bool same_group) {
+    int n = (int)ket.pairs.size();
+    if (ctx->screening) {
+        const double need = ctx->tau / std::max(bra.pairs[i].Q, 1e-300);
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (q_bucket_ceiling(ket.pairs[mid].Q) >= need) lo = mid + 1; else hi = mid; }
+        n = lo;
+    }
+    if (same_group) n = std::min(n, i + 1);
+    return (double)n * per_quartet_cost(bra, ket);
+}
+
+// Per-launch split (see qcf_ctx::launch_split).  Launches in descending modelled cost; one whose bra list gives fewer than
+// split_min_bras pairs per rank goes to the s = nbra / split_min_bras currently least loaded ranks (its bra pairs heaviest
+// first onto the least loaded of those); the launches long enough for every rank follow as one heaviest-first pass over
+// all their (launch, bra) items, which evens out what the short ones left.
+void split_per_launch(qcf_ctx* ctx) {
+    const int W = ctx->world, nl = (int)ctx->plan.size();
+    ctx->launch_split.assign(nl, std::vector<std::vector<int>>(W));
+    std::vector<double> load(W, 0.0);
+    std::vector<int> order(nl);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ctx->plan[x].cost > ctx->plan[y].cost; });
+    struct Item { int l, i; double cost; };
+    std::vector<Item> wide;
+    std::vector<Item> items;
+    for (int l : order) {
+        const PlannedLaunch& pl = ctx->plan[l];
+        const HostGroup& bra = ctx->groups[pl.gi];
+        const HostGroup& ket = ctx->groups[pl.gj];
+        const int nbra = (int)bra.pairs.size();
+        items.clear();
+        for (int i = 0; i < nbra; ++i) items.push_back({l, i, bra_item_cost(ctx, bra, ket, i, pl.gi == pl.gj) + 100.0});
+        const int s = std::max(1, nbra / ctx->split_min_bras);
+        if (s >= W) { wide.insert(wide.end(), items.begin(), items.end()); continue; }
+        std::vector<int> ranks(W);
+        std::iota(ranks.begin(), ranks.end(), 0);
+        std::stable_sort(ranks.begin(), ranks.end(), [&](int x, int y) { return load[x] < load[y]; });
+        ranks.resize(s);
+        std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.cost > y.cost; });
+        for (const Item& it : items) {
+            int r = ranks[0];
+            for (int q : ranks) if (load[q] < load[r]) r = q;
+            load[r] += it.cost;
+            ctx->launch_split[l][r].push_back(it.i);
+        }
+    }
+    std::stable_sort(wide.begin(), wide.end(), [](const Item& x, const Item& y) { return x.cost > y.cost; });
+    for (const Item& it : wide) {
+        const int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        load[r] += it.cost;
+        ctx->launch_split[it.l][r].push_back(it.i);
+    }
+    for (auto& l : ctx->launch_split)
+        for (auto& v : l) std::sort(v.begin(), v.end());
+    ctx->rank_cost = load;
+}
+
 void make_plan(qcf_ctx* ctx) {
     const int ng = (int)ctx->groups.size();
     ctx->plan.clear();
+    ctx->launch_split.clear();
     // Order: the launches whose threads run longest go first (they overlap with everything else), round-robin over the
     // streams.  ps: lanes per shell quartet for the highly contracted launches.
     for (int gi = ng - 1; gi >= 0; --gi)
@@ -611,6 +675,15 @@ void make_plan(qcf_ctx* ctx) {
     }
     for (auto& g : ctx->bra_split)
         for (auto& v : g) std::sort(v.begin(), v.end());
+    if (ctx->split_min_bras > 0) {
+        // keep the per-launch split only if its items are fine enough to balance (small molecules: a few hundred whole
+        // launches cannot be spread evenly over eight ranks; the per-group split always can)
+        const std::vector<double> group_cost = ctx->rank_cost;
+        split_per_launch(ctx);
+        double cmax = 0, csum = 0;
+        for (double c : ctx->rank_cost) { cmax = std::max(cmax, c); csum += c; }
+        if (!(csum > 0) || cmax > 1.01 * csum / W) { ctx->launch_split.clear(); ctx->rank_cost = group_cost; }
+    }
 }
 
 // ---- per-device state ---------------------------------------------------------------------------------
@@ -665,6 +738,15 @@ int setup_device(qcf_ctx* ctx, qcf_device& dv, const std::vector<double>& boys_t
     }
     CK(upload(&dv.all_sa, all_sa));
     CK(upload(&dv.all_sb, all_sb));
+    if (!ctx->launch_split.empty()) {
+        dv.launch_list.assign(ctx->plan.size(), nullptr);
+        dv.launch_nbra.assign(ctx->plan.size(), 0);
+        for (size_t l = 0; l < ctx->plan.size(); ++l) {
+            const auto& list = ctx->launch_split[l][dv.rank];
+            dv.launch_nbra[l] = (int)list.size();
+            if (!list.empty()) CK(upload(&dv.launch_list[l], list));
+        }
+    }
     // opt in to large dynamic shared memory once per device and kernel (not per launch)
     for (int b = 0; b < NPAIRCLASS; ++b)
         for (int k = 0; k <= b; ++k)
@@ -676,6 +758,7 @@ void destroy_device(qcf_device& dv) {
     cudaSetDevice(dv.device);
     cudaDeviceSynchronize();
     for (auto& g : dv.groups) free_group(g);
+    for (int* p : dv.launch_list) cudaFree(p);
     if (dv.graph) cudaGraphExecDestroy(dv.graph);
     cudaFree(dv.boys); cudaFree(dv.fscale); cudaFree(dv.shoff); cudaFree(dv.all_sa); cudaFree(dv.all_sb); cudaFree(dv.all_Dp);
     for (int k = 0; k < 2; ++k) {
@@ -735,17 +818,19 @@ int enqueue_device_work(qcf_ctx* ctx, qcf_device& dv, int mode, const double* pa
         const GroupDev& db = dv.groups[pl.gi];
         const GroupDev& dk = dv.groups[pl.gj];
         const int idx = nl++;
-        if (db.nbra <= 0) continue;
+        const bool per_launch = !dv.launch_nbra.empty();
+        const int nbra = per_launch ? dv.launch_nbra[idx] : db.nbra;
+        if (nbra <= 0) continue;
         const int nket_max = dk.pg.npair;
         const bool slab = bra.la == 2 && bra.lb >= 1;
         const int cta_threads = slab ? 128 : ctx->block;
-        const long long want_chunks = (ctx->target_ctas + db.nbra - 1) / db.nbra;
+        const long long want_chunks = (ctx->target_ctas + nbra - 1) / nbra;
         int kpt = (int)(nket_max / (want_chunks * cta_threads));
         kpt = std::min(kpt, (int)(ctx->serial_cap / pl.serial));
         kpt = std::max(1, std::min(kpt, ctx->kets_per_thread));
         BuildArgs al = a;
         al.counter = dv.counters + idx;
-        al.bra_list = db.bra_list;
+        al.bra_list = per_launch ? dv.launch_list[idx] : db.bra_list;
         int si = ctx->profile ? 0 : (launched % nstr);
         if (ctx->stream_prio != 0 && !ctx->profile && nstr >= 2) {
             // even streams: high priority, odd streams: low priority.  stream_prio 1: block kernels high, slab low; 2: reverse
@@ -757,7 +842,7 @@ int enqueue_device_work(qcf_ctx* ctx, qcf_device& dv, int mode, const double* pa
             while ((int)dv.prof_ev.size() < 2 * (idx + 1)) { cudaEvent_t e; CK(cudaEventCreate(&e)); dv.prof_ev.push_back(e); }
             CK(cudaEventRecord(dv.prof_ev[2 * idx], st));
         }
-        class_table(bra.cls, ket.cls)->jk(nk, pl.ps, db.nbra, nket_max, ctx->block, kpt, st, db.pg, dk.pg, al, pl.gi == pl.gj ? 1 : 0);
+        class_table(bra.cls, ket.cls)->jk(nk, pl.ps, nbra, nket_max, ctx->block, kpt, st, db.pg, dk.pg, al, pl.gi == pl.gj ? 1 : 0);
         if (ctx->profile) CK(cudaEventRecord(dv.prof_ev[2 * idx + 1], st));
         ++launched;
     }
@@ -1060,6 +1145,7 @@ int qcf_create(const qcf_basis* b, const qcf_opts* o, qcf_ctx** out) {
     if (const char* e = getenv("QCF_TARGET_CTAS")) ctx->target_ctas = std::max(1, atoi(e));
     if (const char* e = getenv("QCF_PS_MIN")) ctx->ps_min_prim = std::max(1, atoi(e));
     if (const char* e = getenv("QCF_BLOCK")) ctx->block = atoi(e);
+    if (const char* e = getenv("QCF_SPLIT_MIN_BRAS")) ctx->split_min_bras = std::max(0, atoi(e));
     if (const char* e = getenv("QCF_RED_EPS_FACTOR")) ctx->red_eps_factor = std::max(0.0, atof(e));
     if (const char* e = getenv("QCF_PRIM_CUT")) ctx->prim_cut_factor = std::max(0.0, atof(e));
     if (const char* e = getenv("QCF_PAIR_CUT")) ctx->pair_cut_factor = std::max(0.0, atof(e));

@@ -66,6 +66,8 @@ struct qcf_device {
     cudaGraphExec_t graph = nullptr;
     int graph_mode = -1;
     const double *graph_pa = nullptr, *graph_pb = nullptr;
+    std::vector<int*> launch_list;      // per planned launch: this device's bra indices (per-launch split only)
+    std::vector<int> launch_nbra;
     std::vector<cudaEvent_t> prof_ev;
     int launches = 0;
     float last_ms = 0;
@@ -94,6 +96,11 @@ struct qcf_ctx {
     std::vector<PlannedLaunch> plan;
     std::vector<std::vector<std::vector<int>>> bra_split;   // [group][rank] -> bra indices (cost-balanced)
     std::vector<double> rank_cost;                          // modelled cost per rank
+    // Per-LAUNCH split (split_min_bras > 0, world > 1): a launch whose bra list is too short to fill `world` GPUs is
+    // shared by fewer ranks (at least split_min_bras bra pairs each), so that the ranks run fewer, larger grids; the
+    // long launches are split over all ranks and even out the load.  [plan index][rank] -> bra indices.
+    std::vector<std::vector<std::vector<int>>> launch_split;
+    int split_min_bras = 0;
     double qmax = 0;
     long long prim_total = 0, prim_kept = 0;
     size_t npairs = 0;
