@@ -534,10 +534,11 @@ void tune_launch_shape(qcf_ctx* ctx) {
     int streams = 8, ctas = 296, kpt = ctx->world > 1 ? 32 : 64;
     if (share < 16000) { streams = 32; ctas = 74; kpt = 32; }
     else if (share < 40000) { streams = 16; ctas = 148; }
-    // Bra split: per launch from four ranks on (a launch is shared by as many ranks as get at least 148 bra pairs each; measured
-    // for the eight ranks of an N = 1007 build on one GPU, profiles/r2_ab_call24_per_launch_split.log: slowest rank 9.84 ->
-    // 9.39 ms, every rank faster), per group below
-    if (!getenv("QCF_SPLIT_MIN_BRAS")) ctx->split_min_bras = ctx->world >= 4 ? 148 : 0;
+    // Bra split: per launch from four ranks on -- a launch is split over all ranks only if its bra list has at least 1184
+    // pairs (eight per SM), a shorter one is shared by proportionally fewer ranks (148 pairs per rank at eight ranks, 296 at
+    // four).  Measured rank by rank on one GPU for the N = 1007 build (profiles/r2_ab_call24..., r2_ab_call25...): slowest of
+    // eight ranks 9.83 -> 9.42 ms, slowest of four 19.1 -> 18.0 ms.  Per group below four ranks.
+    if (!getenv("QCF_SPLIT_MIN_BRAS")) ctx->split_min_bras = ctx->world >= 4 ? std::max(1, 1184 / ctx->world) : 0;
     if (!getenv("QCF_STREAMS")) ctx->nstreams = streams;
     if (!getenv("QCF_TARGET_CTAS")) ctx->target_ctas = ctas;
     if (!getenv("QCF_KETS_PER_THREAD")) ctx->kets_per_thread = kpt;
