@@ -185,3 +185,17 @@ def test_cli_occupations_and_parser():
     assert (args.command, args.charge, args.spin_multiplicity, args.max_iterations, args.epsilon) == ("uhf", 1, 2, 50, 1e-6)
     args = cli.build_parser().parse_args(["rhf", "--basis-set", "b.json", "--molecule", "m.json"])
     assert args.max_iterations == 100 and args.backend == "device" and args.gpus == 1
+
+
+def test_every_entry_point_is_bound_by_the_rust_shim_and_documented():
+    """The reference-side binding (rust/qcfock-sys/src/lib.rs, uncompiled here: no Rust toolchain) and INTEGRATION.md
+    must name every function include/qcfock.h declares, so that neither drifts from the C ABI."""
+    import re
+    root = Path(__file__).resolve().parents[1]
+    header = (root / "include" / "qcfock.h").read_text()
+    declared = sorted(set(re.findall(r"\b(qcf_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 25
+    shim = (root / "rust" / "qcfock-sys" / "src" / "lib.rs").read_text()
+    doc = (root / "INTEGRATION.md").read_text()
+    assert [f for f in declared if not re.search(rf"\bfn {f}\s*\(", shim)] == []
+    assert [f for f in declared if f not in doc] == []
